@@ -1,0 +1,544 @@
+// C ABI of libhyperelastic_b200.so (see include/hyperelastic_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Host side only: argument checks, device
+// memory, launches.  There is no CPU compute path in this file by design.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hyperelastic_b200.h"
+#include "hs_kernels.cuh"
+
+using namespace hs;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof b_, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      return fail(HS_ERR_CUDA, b_);                                                                \
+    }                                                                                              \
+  } while (0)
+
+static_assert(sizeof(EosDev) <= sizeof(double) * 20, "EosDev must fit hsd_problem_t::eos_dev");
+static_assert(sizeof(hs_barton2009_t) == sizeof(EosAbi), "ABI struct mismatch");
+
+EosPair eos_pair(const hsd_problem_t* p) {
+  EosPair e;
+  std::memcpy(&e.e[0], p->eos_dev[0], sizeof(EosDev));
+  std::memcpy(&e.e[1], p->eos_dev[1], sizeof(EosDev));
+  return e;
+}
+
+// per-problem scalar block layout inside `scal` (doubles): lam[3][nprob] | t[3][nprob] | steps[nprob] | status
+unsigned long long* scal_lam(double* s) { return reinterpret_cast<unsigned long long*>(s); }
+double* scal_t(double* s, int64_t nprob) { return s + 3 * nprob; }
+long long* scal_steps(double* s, int64_t nprob) { return reinterpret_cast<long long*>(s + 6 * nprob); }
+int* scal_status(double* s, int64_t nprob) { return reinterpret_cast<int*>(s + HS_SCAL_SLOTS * nprob); }
+
+// threads per block of the fused step / sweep kernels
+constexpr int T_STEP_MPH = 128, T_STEP_SP = 128, T_FACE = 64;
+
+template <int MODEL, int FLUX, bool GEN, int T>
+int launch_step_t(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
+  static bool attr_set = false;
+  constexpr size_t smem = step_smem_bytes<T>();
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(k_step<MODEL, FLUX, GEN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_step<MODEL, FLUX, GEN, T><<<(unsigned)nblocks, T, smem, st>>>(a);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+
+template <int MODEL, int T>
+int launch_step_m(int flux, int gen, const StepArgs& a, int64_t nb, cudaStream_t st) {
+  if (flux == HS_FLUX_HLL) return gen ? launch_step_t<MODEL, FLUX_HLL, true, T>(a, nb, st) : launch_step_t<MODEL, FLUX_HLL, false, T>(a, nb, st);
+  return gen ? launch_step_t<MODEL, FLUX_LXF, true, T>(a, nb, st) : launch_step_t<MODEL, FLUX_LXF, false, T>(a, nb, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hs_version(void) { return "hyperelastic_b200 0.1 (sm_100a)"; }
+const char* hs_last_error(void) { return g_err.c_str(); }
+int64_t hs_kernel_launch_count(void) { return g_launches.load(); }
+
+int hs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-pointer layer
+// ---------------------------------------------------------------------------------------------
+int hsd_problem_init(hsd_problem_t* p, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob) {
+  if (!p || !eos) return fail(HS_ERR_ARG, "null argument");
+  if (model != HS_MODEL_SP13 && model != HS_MODEL_MPH30) return fail(HS_ERR_ARG, "unknown model");
+  const int want = model == HS_MODEL_MPH30 ? 2 : 1;
+  if (nphase != want) return fail(HS_ERR_ARG, "nphase must be 2 for MPH30 and 1 for SP13");
+  if (ncells < 3 || nprob < 1) return fail(HS_ERR_ARG, "need ncells >= 3 and nprob >= 1");
+  if (ncells > 0x7fffffff || nprob > 0x7fffffff) return fail(HS_ERR_ARG, "ncells / nprob exceed 2^31-1");
+  std::memset(p, 0, sizeof *p);
+  p->model = model; p->nphase = nphase; p->ncells = ncells; p->nprob = nprob; p->stride = ncells * nprob;
+  p->gen = 0;
+  for (int k = 0; k < 2; ++k) {
+    EosAbi a;
+    std::memcpy(&a, &eos[k < nphase ? k : 0], sizeof a);
+    if (!eos_is_default_exponents(a)) p->gen = 1;
+    EosDev d = make_eos_dev(a);
+    std::memcpy(p->eos_dev[k], &d, sizeof d);
+  }
+  return HS_OK;
+}
+
+int hsd_aos_to_soa(const hsd_problem_t* p, const double* aos, double* soa, void* stream) {
+  const long long n = p->stride;
+  constexpr int TC = 64;
+  const unsigned nb = (unsigned)((n + TC - 1) / TC);
+  if (p->model == HS_MODEL_MPH30) k_aos_to_soa<30, TC><<<nb, 256, 0, (cudaStream_t)stream>>>(aos, soa, n, p->stride);
+  else k_aos_to_soa<13, TC><<<nb, 256, 0, (cudaStream_t)stream>>>(aos, soa, n, p->stride);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+
+int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa, double* aos, void* stream) {
+  const long long n = p->stride;
+  constexpr int TC = 64;
+  const unsigned nb = (unsigned)((n + TC - 1) / TC);
+  if (p->model == HS_MODEL_MPH30) k_soa_to_aos<30, TC><<<nb, 256, 0, (cudaStream_t)stream>>>(soa, aos, n, p->stride);
+  else k_soa_to_aos<13, TC><<<nb, 256, 0, (cudaStream_t)stream>>>(soa, aos, n, p->stride);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+
+static int wave_bounds_impl(const hsd_problem_t* p, const double* Q, double* lo, double* hi, double* scal, int slot,
+                            double* eig_full, cudaStream_t st) {
+  if (slot < 0 || slot > 2) return fail(HS_ERR_ARG, "slot must be 0..2");
+  unsigned long long* lam = scal_lam(scal) + (size_t)slot * p->nprob;
+  CU(cudaMemsetAsync(lam, 0, sizeof(double) * p->nprob, st));
+  int* status = scal_status(scal, p->nprob);
+  const EosPair e = eos_pair(p);
+  constexpr int T = 128;
+  const int cpb = T / p->nphase;
+  const int tiles = (int)((p->ncells + cpb - 1) / cpb);
+  const unsigned nb = (unsigned)(tiles * p->nprob);
+  if (p->model == HS_MODEL_MPH30) {
+    if (p->gen) k_bounds<MODEL_MPH30, true, T><<<nb, T, 0, st>>>(Q, lo, hi, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
+    else k_bounds<MODEL_MPH30, false, T><<<nb, T, 0, st>>>(Q, lo, hi, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
+  } else {
+    if (p->gen) k_bounds<MODEL_SP13, true, T><<<nb, T, 0, st>>>(Q, lo, hi, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
+    else k_bounds<MODEL_SP13, false, T><<<nb, T, 0, st>>>(Q, lo, hi, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
+  }
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+
+int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* lo, double* hi, double* scal, int slot, void* stream) {
+  return wave_bounds_impl(p, Q, lo, hi, scal, slot, nullptr, (cudaStream_t)stream);
+}
+
+int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
+             const double* lo_in, const double* hi_in, double* Qout, double* lo_out, double* hi_out, double* scal,
+             double* dt_hist, int64_t hist_k, int64_t hist_cap, void* stream) {
+  if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
+  StepArgs a;
+  a.Qin = Qin; a.Qout = Qout; a.lo_in = lo_in; a.hi_in = hi_in; a.lo_out = lo_out; a.hi_out = hi_out;
+  a.lam = scal_lam(scal); a.tt = scal_t(scal, p->nprob); a.steps = scal_steps(scal, p->nprob);
+  a.status = scal_status(scal, p->nprob);
+  a.dt_hist = dt_hist; a.hist_k = hist_k; a.hist_cap = dt_hist ? hist_cap : 0;
+  a.stride = p->stride; a.ncells = (int)p->ncells; a.nprob = (int)p->nprob;
+  a.cur = (int)(n % 3); a.nxt = (int)((n + 1) % 3); a.clr = (int)((n + 2) % 3);
+  a.cfl = cfl; a.dx = dx; a.t_end = t_end;
+  a.eos = eos_pair(p);
+  if (p->model == HS_MODEL_MPH30) {
+    constexpr int T = T_STEP_MPH, CPB = T / 2;
+    a.tiles_per_prob = (int)((p->ncells - 2 + (CPB - 2) - 1) / (CPB - 2));
+    return launch_step_m<MODEL_MPH30, T>(flux, p->gen, a, (int64_t)a.tiles_per_prob * p->nprob, (cudaStream_t)stream);
+  } else {
+    constexpr int T = T_STEP_SP, CPB = T;
+    a.tiles_per_prob = (int)((p->ncells - 2 + (CPB - 2) - 1) / (CPB - 2));
+    return launch_step_m<MODEL_SP13, T>(flux, p->gen, a, (int64_t)a.tiles_per_prob * p->nprob, (cudaStream_t)stream);
+  }
+}
+
+double* hsd_scal_lambda_next(double* scal, int64_t nprob, int64_t n) { return scal + ((n + 1) % 3) * nprob; }
+double* hsd_scal_lambda_cur(double* scal, int64_t nprob, int64_t n) { return scal + (n % 3) * nprob; }
+double* hsd_scal_time(double* scal, int64_t nprob, int64_t n) { return scal + 3 * nprob + (n % 3) * nprob; }
+double* hsd_scal_steps(double* scal, int64_t nprob) { return scal + 6 * nprob; }
+double* hsd_scal_status(double* scal, int64_t nprob) { return scal + HS_SCAL_SLOTS * nprob; }
+
+// ---------------------------------------------------------------------------------------------
+// stateful context (host-buffer ABI)
+// ---------------------------------------------------------------------------------------------
+struct hs_ctx {
+  hsd_problem_t prob;
+  int device;
+  int nvar;
+  cudaStream_t stream;
+  double* Q[2];
+  double* lo[2];
+  double* hi[2];
+  double* scal;
+  double* stage;      // AoS staging, nvar*stride doubles
+  double* dt_hist;    // device, grown on demand
+  int64_t hist_cap;
+  int64_t n;          // launch counter since the last upload (selects buffers and scalar slots)
+};
+
+static int ctx_enter(hs_ctx* c) {
+  if (!c) return fail(HS_ERR_ARG, "null context");
+  CU(cudaSetDevice(c->device));
+  return HS_OK;
+}
+
+int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob, int device) {
+  if (!out) return fail(HS_ERR_ARG, "null ctx pointer");
+  *out = nullptr;
+  if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  hs_ctx* c = new hs_ctx();
+  std::memset(c, 0, sizeof *c);
+  int rc = hsd_problem_init(&c->prob, model, eos, nphase, ncells, nprob);
+  if (rc) { delete c; return rc; }
+  c->device = device;
+  c->nvar = model == HS_MODEL_MPH30 ? 30 : 13;
+  auto bail = [&](int code) { hs_destroy(c); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail(HS_ERR_CUDA, "cudaSetDevice failed"); }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(HS_ERR_CUDA, "stream creation failed"); }
+  const size_t nq = (size_t)c->nvar * c->prob.stride * sizeof(double), nb = (size_t)c->prob.stride * sizeof(double);
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    e = cudaMalloc(&c->Q[k], nq);
+    if (e == cudaSuccess) e = cudaMalloc(&c->lo[k], nb);
+    if (e == cudaSuccess) e = cudaMalloc(&c->hi[k], nb);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&c->scal, sizeof(double) * HS_SCAL_DOUBLES(nprob));
+  if (e == cudaSuccess) e = cudaMemset(c->scal, 0, sizeof(double) * HS_SCAL_DOUBLES(nprob));
+  if (e != cudaSuccess) { g_err = std::string("device allocation failed: ") + cudaGetErrorString(e); return bail(HS_ERR_CUDA); }
+  *out = c;
+  return HS_OK;
+}
+
+int hs_destroy(hs_ctx_t* c) {
+  if (!c) return HS_OK;
+  cudaSetDevice(c->device);
+  for (int k = 0; k < 2; ++k) { cudaFree(c->Q[k]); cudaFree(c->lo[k]); cudaFree(c->hi[k]); }
+  cudaFree(c->scal); cudaFree(c->stage); cudaFree(c->dt_hist);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return HS_OK;
+}
+
+static int ensure_stage(hs_ctx* c) {
+  if (!c->stage) CU(cudaMalloc(&c->stage, (size_t)c->nvar * c->prob.stride * sizeof(double)));
+  return HS_OK;
+}
+
+static int read_status(hs_ctx* c) {
+  int st = 0;
+  CU(cudaMemcpyAsync(&st, scal_status(c->scal, c->prob.nprob), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (st) return fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError");
+  return HS_OK;
+}
+
+int hs_upload(hs_ctx_t* c, const double* Q) {
+  int rc = ctx_enter(c); if (rc) return rc;
+  if (!Q) return fail(HS_ERR_ARG, "null Q");
+  rc = ensure_stage(c); if (rc) return rc;
+  const size_t nq = (size_t)c->nvar * c->prob.stride * sizeof(double);
+  CU(cudaMemcpyAsync(c->stage, Q, nq, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->scal, 0, sizeof(double) * HS_SCAL_DOUBLES(c->prob.nprob), c->stream));
+  c->n = 0;
+  rc = hsd_aos_to_soa(&c->prob, c->stage, c->Q[0], c->stream); if (rc) return rc;
+  rc = hsd_wave_bounds(&c->prob, c->Q[0], c->lo[0], c->hi[0], c->scal, 0, c->stream); if (rc) return rc;
+  return read_status(c);
+}
+
+int hs_download(hs_ctx_t* c, double* Q) {
+  int rc = ctx_enter(c); if (rc) return rc;
+  if (!Q) return fail(HS_ERR_ARG, "null Q");
+  rc = ensure_stage(c); if (rc) return rc;
+  rc = hsd_soa_to_aos(&c->prob, c->Q[c->n & 1], c->stage, c->stream); if (rc) return rc;
+  CU(cudaMemcpyAsync(Q, c->stage, (size_t)c->nvar * c->prob.stride * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return HS_OK;
+}
+
+int hs_set_time(hs_ctx_t* c, double t, int64_t step) {
+  int rc = ctx_enter(c); if (rc) return rc;
+  const int64_t np = c->prob.nprob;
+  std::vector<double> tv(np, t);
+  std::vector<long long> sv(np, step);
+  CU(cudaMemcpyAsync(hsd_scal_time(c->scal, np, c->n), tv.data(), sizeof(double) * np, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(scal_steps(c->scal, np), sv.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return HS_OK;
+}
+
+int hs_wave_speeds(hs_ctx_t* c, double* eig, double* lambda_max) {
+  int rc = ctx_enter(c); if (rc) return rc;
+  const int64_t np = c->prob.nprob;
+  const int cur = (int)(c->n & 1);
+  if (eig) {
+    const size_t ne = (size_t)6 * c->prob.nphase * c->prob.stride * sizeof(double);
+    double* d_eig = nullptr;
+    CU(cudaMalloc(&d_eig, ne));
+    // recompute into the current slot (same values: the sweep is deterministic and max is exact)
+    rc = wave_bounds_impl(&c->prob, c->Q[cur], c->lo[cur], c->hi[cur], c->scal, (int)(c->n % 3), d_eig, c->stream);
+    if (rc == HS_OK && cudaMemcpyAsync(eig, d_eig, ne, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = fail(HS_ERR_CUDA, "eig download failed");
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_eig);
+    if (rc) return rc;
+  }
+  if (lambda_max) {
+    CU(cudaMemcpyAsync(lambda_max, hsd_scal_lambda_cur(c->scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return read_status(c);
+}
+
+static int enqueue_step(hs_ctx* c, int flux, double cfl, double dx, double t_end, double* hist, int64_t hist_k, int64_t hist_cap) {
+  const int a = (int)(c->n & 1), b = a ^ 1;
+  int rc = hsd_step(&c->prob, flux, cfl, dx, t_end, c->n, c->Q[a], c->lo[a], c->hi[a], c->Q[b], c->lo[b], c->hi[b], c->scal,
+                    hist, hist_k, hist_cap, c->stream);
+  if (rc == HS_OK) c->n += 1;
+  return rc;
+}
+
+static int ensure_hist(hs_ctx* c, int64_t cap) {
+  if (c->hist_cap >= cap && c->dt_hist) return HS_OK;
+  if (c->dt_hist) { cudaFree(c->dt_hist); c->dt_hist = nullptr; }
+  CU(cudaMalloc(&c->dt_hist, sizeof(double) * cap * c->prob.nprob));
+  c->hist_cap = cap;
+  return HS_OK;
+}
+
+int hs_step(hs_ctx_t* c, int flux, double cfl, double dx, double* dt_out) {
+  int rc = ctx_enter(c); if (rc) return rc;
+  rc = ensure_hist(c, 1); if (rc) return rc;
+  const int64_t np = c->prob.nprob;
+  rc = enqueue_step(c, flux, cfl, dx, 1.0e300, c->dt_hist, 0, 1); if (rc) return rc;
+  if (dt_out) CU(cudaMemcpyAsync(dt_out, c->dt_hist, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+  return read_status(c);
+}
+
+int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64_t max_steps, double* t_io,
+               int64_t* step_io, double* dt_hist) {
+  int rc = ctx_enter(c); if (rc) return rc;
+  if (max_steps < 0) return fail(HS_ERR_ARG, "max_steps < 0");
+  const int64_t np = c->prob.nprob;
+  if (t_io) CU(cudaMemcpyAsync(hsd_scal_time(c->scal, np, c->n), t_io, sizeof(double) * np, cudaMemcpyHostToDevice, c->stream));
+  if (step_io) CU(cudaMemcpyAsync(scal_steps(c->scal, np), step_io, sizeof(long long) * np, cudaMemcpyHostToDevice, c->stream));
+  double* hist = nullptr;
+  if (dt_hist && max_steps > 0) {
+    rc = ensure_hist(c, max_steps); if (rc) return rc;
+    CU(cudaMemsetAsync(c->dt_hist, 0, sizeof(double) * max_steps * np, c->stream));
+    hist = c->dt_hist;
+  }
+  std::vector<double> tv(np);
+  int64_t done = 0;
+  const int64_t batch = 32;
+  while (done < max_steps) {
+    // all problems finished?  (the kernels are no-ops past t_end, so over-launching is harmless)
+    CU(cudaMemcpyAsync(tv.data(), hsd_scal_time(c->scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    bool any = false;
+    for (int64_t i = 0; i < np; ++i) if (tv[i] < t_end) { any = true; break; }
+    if (!any) break;
+    const int64_t m = (max_steps - done < batch) ? (max_steps - done) : batch;
+    for (int64_t k = 0; k < m; ++k) { rc = enqueue_step(c, flux, cfl, dx, t_end, hist, done + k, max_steps); if (rc) return rc; }
+    done += m;
+  }
+  if (t_io) CU(cudaMemcpyAsync(t_io, hsd_scal_time(c->scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+  if (step_io) CU(cudaMemcpyAsync(step_io, scal_steps(c->scal, np), sizeof(long long) * np, cudaMemcpyDeviceToHost, c->stream));
+  if (hist) CU(cudaMemcpyAsync(dt_hist, c->dt_hist, sizeof(double) * max_steps * np, cudaMemcpyDeviceToHost, c->stream));
+  return read_status(c);
+}
+
+int hs_step_host(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin, double* Qout, double* dt_out) {
+  int rc = hs_upload(c, Qin); if (rc && rc != HS_ERR_DOMAIN) return rc;
+  int rc2 = hs_step(c, flux, cfl, dx, dt_out); if (rc2 && rc2 != HS_ERR_DOMAIN) return rc2;
+  int rc3 = hs_download(c, Qout); if (rc3) return rc3;
+  return rc ? rc : rc2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stateless batches
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+struct DevBuf {
+  double* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n * sizeof(double)); }
+};
+
+int stateless_prolog(int model, const hs_barton2009_t* eos, int nphase, int64_t n, int device, hsd_problem_t* p) {
+  if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  if (n < 1) return fail(HS_ERR_ARG, "n < 1");
+  int rc = hsd_problem_init(p, model, eos, nphase, 3, 1);
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  return HS_OK;
+}
+
+template <int OP>
+int cellop(int model, const hs_barton2009_t* eos, int nphase, const double* in, double* out, int64_t n, int device) {
+  hsd_problem_t p;
+  int rc = stateless_prolog(model, eos, nphase, n, device, &p); if (rc) return rc;
+  if (!in || !out) return fail(HS_ERR_ARG, "null array");
+  const int nvar = model == HS_MODEL_MPH30 ? 30 : 13;
+  DevBuf din, dout, dst;
+  CU(din.alloc((size_t)nvar * n)); CU(dout.alloc((size_t)nvar * n)); CU(dst.alloc(1));
+  CU(cudaMemcpy(din.p, in, sizeof(double) * nvar * n, cudaMemcpyHostToDevice));
+  CU(cudaMemset(dst.p, 0, sizeof(double)));
+  const EosPair e = eos_pair(&p);
+  const unsigned nb = (unsigned)((n * nphase + 127) / 128);
+  int* st = reinterpret_cast<int*>(dst.p);
+  if (model == HS_MODEL_MPH30) {
+    if (p.gen) k_cellop<MODEL_MPH30, true, OP><<<nb, 128>>>(din.p, dout.p, n, e, st);
+    else k_cellop<MODEL_MPH30, false, OP><<<nb, 128>>>(din.p, dout.p, n, e, st);
+  } else {
+    if (p.gen) k_cellop<MODEL_SP13, true, OP><<<nb, 128>>>(din.p, dout.p, n, e, st);
+    else k_cellop<MODEL_SP13, false, OP><<<nb, 128>>>(din.p, dout.p, n, e, st);
+  }
+  g_launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dout.p, sizeof(double) * nvar * n, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  CU(cudaMemcpy(&bad, st, sizeof(int), cudaMemcpyDeviceToHost));
+  return bad ? fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError") : HS_OK;
+}
+
+template <int MODEL, int FLUX>
+int faceop_launch(const hsd_problem_t& p, const double* ql, const double* qr, const double* el, const double* er, double lambda,
+                  double* cons, double* dm, double* dp, double* s, int64_t n, int* st) {
+  constexpr int T = T_FACE;
+  const size_t smem = sizeof(double) * 75 * T;
+  const EosPair e = eos_pair(&p);
+  const unsigned nb = (unsigned)((n * ModelTraits<MODEL>::NPH + T - 1) / T);
+  if (p.gen) k_faceop<MODEL, FLUX, true, T><<<nb, T, smem>>>(ql, qr, el, er, lambda, cons, dm, dp, s, n, e, st);
+  else k_faceop<MODEL, FLUX, false, T><<<nb, T, smem>>>(ql, qr, el, er, lambda, cons, dm, dp, s, n, e, st);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+
+int faceop(int model, int flux, const hs_barton2009_t* eos, int nphase, const double* Ql, const double* Qr, const double* eig_l,
+           const double* eig_r, double lambda, double* cons, double* dm, double* dp, double* s, int64_t n, int device) {
+  hsd_problem_t p;
+  int rc = stateless_prolog(model, eos, nphase, n, device, &p); if (rc) return rc;
+  if (!Ql || !Qr) return fail(HS_ERR_ARG, "null array");
+  if (flux == HS_FLUX_HLL && (!eig_l || !eig_r)) return fail(HS_ERR_ARG, "hll needs the cached eigvals of both cells");
+  const int nvar = model == HS_MODEL_MPH30 ? 30 : 13, neig = 6 * nphase;
+  DevBuf dl, dr, del, der, dc, dmm, dpp, ds, dst;
+  CU(dl.alloc((size_t)nvar * n)); CU(dr.alloc((size_t)nvar * n));
+  CU(dc.alloc((size_t)nvar * n)); CU(dmm.alloc((size_t)nvar * n)); CU(dpp.alloc((size_t)nvar * n));
+  CU(ds.alloc((size_t)2 * n)); CU(dst.alloc(1));
+  CU(cudaMemcpy(dl.p, Ql, sizeof(double) * nvar * n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dr.p, Qr, sizeof(double) * nvar * n, cudaMemcpyHostToDevice));
+  if (flux == HS_FLUX_HLL) {
+    CU(del.alloc((size_t)neig * n)); CU(der.alloc((size_t)neig * n));
+    CU(cudaMemcpy(del.p, eig_l, sizeof(double) * neig * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(der.p, eig_r, sizeof(double) * neig * n, cudaMemcpyHostToDevice));
+  }
+  CU(cudaMemset(dst.p, 0, sizeof(double)));
+  CU(cudaMemset(ds.p, 0, sizeof(double) * 2 * n));
+  int* st = reinterpret_cast<int*>(dst.p);
+  if (model == HS_MODEL_MPH30) {
+    rc = flux == HS_FLUX_HLL ? faceop_launch<MODEL_MPH30, FLUX_HLL>(p, dl.p, dr.p, del.p, der.p, lambda, dc.p, dmm.p, dpp.p, ds.p, n, st)
+                             : faceop_launch<MODEL_MPH30, FLUX_LXF>(p, dl.p, dr.p, del.p, der.p, lambda, dc.p, dmm.p, dpp.p, ds.p, n, st);
+  } else {
+    rc = flux == HS_FLUX_HLL ? faceop_launch<MODEL_SP13, FLUX_HLL>(p, dl.p, dr.p, del.p, der.p, lambda, dc.p, dmm.p, dpp.p, ds.p, n, st)
+                             : faceop_launch<MODEL_SP13, FLUX_LXF>(p, dl.p, dr.p, del.p, der.p, lambda, dc.p, dmm.p, dpp.p, ds.p, n, st);
+  }
+  if (rc) return rc;
+  if (cons) CU(cudaMemcpy(cons, dc.p, sizeof(double) * nvar * n, cudaMemcpyDeviceToHost));
+  if (dm) CU(cudaMemcpy(dm, dmm.p, sizeof(double) * nvar * n, cudaMemcpyDeviceToHost));
+  if (dp) CU(cudaMemcpy(dp, dpp.p, sizeof(double) * nvar * n, cudaMemcpyDeviceToHost));
+  if (s) CU(cudaMemcpy(s, ds.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  CU(cudaMemcpy(&bad, st, sizeof(int), cudaMemcpyDeviceToHost));
+  return bad ? fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError") : HS_OK;
+}
+}  // namespace
+
+extern "C" {
+int hs_cons2prim(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* P, int64_t n, int device) {
+  return cellop<OP_CONS2PRIM>(model, eos, nphase, Q, P, n, device);
+}
+int hs_prim2cons(int model, const hs_barton2009_t* eos, int nphase, const double* P, double* Q, int64_t n, int device) {
+  return cellop<OP_PRIM2CONS>(model, eos, nphase, P, Q, n, device);
+}
+int hs_flux(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* F, int64_t n, int device) {
+  return cellop<OP_FLUX>(model, eos, nphase, Q, F, n, device);
+}
+
+int hs_noncons_flux(const hs_barton2009_t* eos, const double* Q, double* col, double* Bdense, int64_t n, int device) {
+  std::vector<double> tmp;
+  double* c = col;
+  if (!c) { tmp.resize((size_t)30 * n); c = tmp.data(); }
+  int rc = cellop<OP_NONCONS>(HS_MODEL_MPH30, eos, 2, Q, c, n, device);
+  if (rc && rc != HS_ERR_DOMAIN) return rc;
+  if (Bdense) {  // block-diagonal, only column 1 of each block is non-zero (HyperelasticityMPh.jl:221-248)
+    std::memset(Bdense, 0, sizeof(double) * 900 * n);
+    for (int64_t i = 0; i < n; ++i)
+      for (int p = 0; p < 2; ++p)
+        for (int r = 0; r < 15; ++r) Bdense[900 * i + (15 * p + r) + 30 * (15 * p)] = c[30 * i + 15 * p + r];
+  }
+  return rc;
+}
+
+int hs_get_eigvals(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* eig, int64_t n, int device) {
+  hsd_problem_t p;
+  int rc = stateless_prolog(model, eos, nphase, n, device, &p); if (rc) return rc;
+  if (!Q || !eig) return fail(HS_ERR_ARG, "null array");
+  const int nvar = model == HS_MODEL_MPH30 ? 30 : 13, neig = 6 * nphase;
+  DevBuf din, dout, dst;
+  CU(din.alloc((size_t)nvar * n)); CU(dout.alloc((size_t)neig * n)); CU(dst.alloc(1));
+  CU(cudaMemcpy(din.p, Q, sizeof(double) * nvar * n, cudaMemcpyHostToDevice));
+  CU(cudaMemset(dst.p, 0, sizeof(double)));
+  const EosPair e = eos_pair(&p);
+  const unsigned nb = (unsigned)((n * nphase + 127) / 128);
+  int* st = reinterpret_cast<int*>(dst.p);
+  if (model == HS_MODEL_MPH30) {
+    if (p.gen) k_eigvals<MODEL_MPH30, true><<<nb, 128>>>(din.p, dout.p, n, e, st); else k_eigvals<MODEL_MPH30, false><<<nb, 128>>>(din.p, dout.p, n, e, st);
+  } else {
+    if (p.gen) k_eigvals<MODEL_SP13, true><<<nb, 128>>>(din.p, dout.p, n, e, st); else k_eigvals<MODEL_SP13, false><<<nb, 128>>>(din.p, dout.p, n, e, st);
+  }
+  g_launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(eig, dout.p, sizeof(double) * neig * n, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  CU(cudaMemcpy(&bad, st, sizeof(int), cudaMemcpyDeviceToHost));
+  return bad ? fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError") : HS_OK;
+}
+
+int hs_hll(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, const double* Qr, const double* eig_l,
+           const double* eig_r, double* cons, double* dm, double* dp, double* s, int64_t n, int device) {
+  return faceop(model, HS_FLUX_HLL, eos, nphase, Ql, Qr, eig_l, eig_r, 0.0, cons, dm, dp, s, n, device);
+}
+int hs_lxf(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, const double* Qr, double lambda, double* cons,
+           double* dm, double* dp, int64_t n, int device) {
+  return faceop(model, HS_FLUX_LXF, eos, nphase, Ql, Qr, nullptr, nullptr, lambda, cons, dm, dp, nullptr, n, device);
+}
+
+}  // extern "C"

@@ -1,0 +1,651 @@
+// Device kernels of the finite-volume hot path (sm_100a, FP64, structure-of-arrays).
+//
+// Work decomposition: one thread per (cell, phase).  The two phases of a cell sit in adjacent
+// lanes, so the only cross-phase coupling of the model -- the interface velocity / interface
+// stress of the non-conservative matrix (HyperelasticityMPh.jl:212-217) and the min/max of the
+// wave bounds over phases -- is a lane-xor-1 shuffle.  The single-phase model is the same code
+// with one thread per cell.
+//
+// k_step is ONE kernel per time step (main.jl:204-227 fused):
+//   load tile (+1 halo cell each side) -> per-cell state + physical flux (shared memory)
+//   -> per-face HLL / LxF path-conservative fluctuations (3 x 6 quadrature states per face for
+//      HLL, each evaluated once instead of the reference's twice) -> conservative update
+//   -> wave bounds of the NEW state + block max + one atomicMax per block, which is the
+//      lambda_max that the NEXT step's dt = cfl dx / lambda_max needs.
+// Intermediate fields (primitives, stress, fluxes, Q_hll, fluctuations) never touch HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hs_phase.cuh"
+
+namespace hs {
+
+constexpr int MODEL_SP13 = 0, MODEL_MPH30 = 1;
+constexpr int FLUX_LXF = 0, FLUX_HLL = 1;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct EosPair { EosDev e[2]; };
+
+// gausslegendre(6) / gausslobatto(6) mapped to [0,1] as NumFluxes.jl:95 / :37 do.
+__constant__ double c_gleg_x[6] = {(-0.9324695142031520278 + 1.0) / 2.0, (-0.6612093864662645137 + 1.0) / 2.0,
+                                   (-0.2386191860831969086 + 1.0) / 2.0, (0.2386191860831969086 + 1.0) / 2.0,
+                                   (0.6612093864662645137 + 1.0) / 2.0,  (0.9324695142031520278 + 1.0) / 2.0};
+__constant__ double c_gleg_w[6] = {0.1713244923791703450 / 2.0, 0.3607615730481386076 / 2.0, 0.4679139345726910474 / 2.0,
+                                   0.4679139345726910474 / 2.0, 0.3607615730481386076 / 2.0, 0.1713244923791703450 / 2.0};
+__constant__ double c_glob_x[6] = {(-1.0 + 1.0) / 2.0, (-0.7650553239294646929 + 1.0) / 2.0, (-0.2852315164806450963 + 1.0) / 2.0,
+                                   (0.2852315164806450963 + 1.0) / 2.0, (0.7650553239294646929 + 1.0) / 2.0, (1.0 + 1.0) / 2.0};
+__constant__ double c_glob_w[6] = {0.06666666666666666667 / 2.0, 0.3784749562978469803 / 2.0, 0.5548583770354863530 / 2.0,
+                                   0.5548583770354863530 / 2.0,  0.3784749562978469803 / 2.0, 0.06666666666666666667 / 2.0};
+
+// Canonical per-phase record (15 slots): 0 alpha, 1 alpha*rho, 2-4 momentum, 5 energy,
+// 6-14 A = alpha*rho*F column-major.  SP13 variable v lives in slot sp_slot(v); slots 0,1 unused.
+__host__ __device__ constexpr int sp_slot(int v) { return v < 3 ? 2 + v : (v == 12 ? 5 : 6 + ((v - 3) / 3) + 3 * ((v - 3) % 3)); }
+
+template <int MODEL> struct ModelTraits;
+template <> struct ModelTraits<MODEL_SP13> { static constexpr int NPH = 1, NVAR = 13, J0 = 2; };
+template <> struct ModelTraits<MODEL_MPH30> { static constexpr int NPH = 2, NVAR = 30, J0 = 0; };
+
+// state of the record stored in a shared-memory column (row stride T)
+template <int MODEL, bool GEN, int T>
+__device__ __forceinline__ void column_state(const EosDev& eos, const double* col, PhaseState& st) {
+  double m[3] = {col[2 * T], col[3 * T], col[4 * T]};
+  double A[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) A[k] = col[(6 + k) * T];
+  const double alpha = (MODEL == MODEL_MPH30) ? col[0] : 1.0;
+  phase_state<GEN>(eos, alpha, m, col[5 * T], A, st);
+}
+
+// Column 1 of the non-conservative block of this thread's phase at one state (the other phase's
+// temperature, velocity and stress come from the adjacent lane).  HyperelasticityMPh.jl:212-230
+// with omega = 0, k = (1/2, 1/2), beta = 0.  c[1] (the alpha*rho row) is identically zero.
+__device__ __forceinline__ void noncons_column(const PhaseState& st, const double* A, double* c) {
+  const double To = __shfl_xor_sync(FULL, st.T, 1);
+  double uo[3], so[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { uo[k] = __shfl_xor_sync(FULL, st.u[k], 1); so[k] = __shfl_xor_sync(FULL, st.sig1[k], 1); }
+  const double uI[3] = {0.5 * st.u[0] + 0.5 * uo[0], 0.5 * st.u[1] + 0.5 * uo[1], 0.5 * st.u[2] + 0.5 * uo[2]};  // :213
+  const double inv = 1.0 / (st.T + To);
+  const double sI[3] = {(To * st.sig1[0] + st.T * so[0]) * inv, (To * st.sig1[1] + st.T * so[1]) * inv,
+                        (To * st.sig1[2] + st.T * so[2]) * inv};                                            // :217
+  c[0] = uI[0];                                                                                              // :223
+  c[1] = 0.0;
+  c[2] = sI[0]; c[3] = sI[1]; c[4] = sI[2];                                                                  // :224
+  c[5] = sI[0] * uI[0] + sI[1] * uI[1] + sI[2] * uI[2];                                                      // :225
+  const double dv[3] = {uI[0] - st.u[0], uI[1] - st.u[1], uI[2] - st.u[2]};
+  const double ia = st.inv_alpha;  // rho F = A / alpha
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double rF1j = A[3 * j] * ia;
+    c[6 + 3 * j] = rF1j * st.u[0] + ia * (A[3 * j] * dv[0] + A[3 * j + 1] * dv[1] + A[3 * j + 2] * dv[2]);   // :228,:230
+    c[7 + 3 * j] = rF1j * st.u[1];
+    c[8 + 3 * j] = rF1j * st.u[2];
+  }
+}
+
+// acc[j] += dalpha * sum_q w_q c_j(psi(s_q)),  psi(s) = a (1-s) + b s        (NumFluxes.jl:97-107)
+// a, b: shared-memory columns (row stride T) of this thread's phase.  MPh only.
+template <bool GEN, int T>
+__device__ __forceinline__ void path_integral(const EosDev& eos, const double* a, const double* b, const double* xs,
+                                              const double* ws, double* acc, int& bad) {
+  const double dalpha = b[0] - a[0];
+#pragma unroll 1
+  for (int q = 0; q < 6; ++q) {
+    const double s = xs[q], oms = 1.0 - s, w = ws[q] * dalpha;
+    const double alpha = a[0] * oms + b[0] * s;
+    double m[3], A[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) m[k] = a[(2 + k) * T] * oms + b[(2 + k) * T] * s;
+    const double E = a[5 * T] * oms + b[5 * T] * s;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A[k] = a[(6 + k) * T] * oms + b[(6 + k) * T] * s;
+    PhaseState st;
+    phase_state<GEN>(eos, alpha, m, E, A, st);
+    bad |= st.bad;
+    double c[15];
+    noncons_column(st, A, c);
+#pragma unroll
+    for (int j = 0; j < 15; ++j)
+      if (j != 1) acc[j] += w * c[j];
+  }
+}
+
+// One face between the records in columns a (left) and b (right) with their physical fluxes Fa, Fb.
+// lo_l / hi_r: cached wave bounds of the left / right cell (the `eigvals` argument of hll,
+// NumFluxes.jl:90-91).  H: this thread's private scratch column (Q_hll).  For every slot j the
+// functor receives (j, cons, dm, dp) = the three return values of hll / lxf for that component.
+template <int MODEL, int FLUX, bool GEN, int T, class Emit>
+__device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, const double* b, const double* Fa,
+                                          const double* Fb, double lo_l, double hi_r, double lambda, double* H,
+                                          int& bad, double* s_out, Emit emit) {
+  constexpr int J0 = ModelTraits<MODEL>::J0;
+  constexpr bool MPH = MODEL == MODEL_MPH30;
+  if (FLUX == FLUX_HLL) {
+    // wave-speed bounds at Q_m = (Q_l + Q_r)/2, NumFluxes.jl:86-91
+    double s_l, s_r;
+    {
+      double m[3], A[9];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) m[k] = 0.5 * (a[(2 + k) * T] + b[(2 + k) * T]);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) A[k] = 0.5 * (a[(6 + k) * T] + b[(6 + k) * T]);
+      const double alpha = MPH ? 0.5 * (a[0] + b[0]) : 1.0;
+      PhaseState sm;
+      phase_state<GEN>(eos, alpha, m, 0.5 * (a[5 * T] + b[5 * T]), A, sm);
+      bad |= sm.bad;
+      const double cm = phase_cmax(eos, sm);
+      double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
+      if (MPH) {
+        lo_m = fmin(lo_m, __shfl_xor_sync(FULL, lo_m, 1));
+        hi_m = fmax(hi_m, __shfl_xor_sync(FULL, hi_m, 1));
+      }
+      s_l = fmin(0.0, fmin(lo_m, lo_l));
+      s_r = fmax(0.0, fmax(hi_m, hi_r));
+    }
+    if (s_out) { s_out[0] = s_l; s_out[1] = s_r; }
+    const double inv_ds = 1.0 / (s_r - s_l);
+    const double k_q = s_l * s_r * inv_ds;
+    if (MPH) {
+      double acc[15];
+#pragma unroll
+      for (int j = 0; j < 15; ++j) acc[j] = 0.0;
+      path_integral<GEN, T>(eos, a, b, c_gleg_x, c_gleg_w, acc, bad);                 // B_int(Q_l, Q_r)
+#pragma unroll
+      for (int j = 0; j < 15; ++j) {
+        if (j == 1) continue;  // alpha*rho is never read by the physics
+        const double path = (acc[j] + Fb[j * T]) - Fa[j * T];                         // :109
+        H[j * T] = ((b[j * T] * s_r - a[j * T] * s_l) - path) * inv_ds;               // :111  Q_hll
+        acc[j] = 0.0;
+      }
+      path_integral<GEN, T>(eos, a, H, c_gleg_x, c_gleg_w, acc, bad);                 // B_int(Q_l, Q_hll)
+      path_integral<GEN, T>(eos, H, b, c_gleg_x, c_gleg_w, acc, bad);                 // B_int(Q_hll, Q_r)
+      const double k_m = -s_l * inv_ds, k_p = s_r * inv_ds;
+#pragma unroll
+      for (int j = 0; j < 15; ++j) {                                                   // :128-129
+        const double br = (Fb[j * T] - Fa[j * T]) + (j == 1 ? 0.0 : acc[j]);
+        const double dq = k_q * (b[j * T] - a[j * T]);
+        emit(j, 0.0, k_m * br + dq, k_p * br - dq);
+      }
+    } else {
+#pragma unroll
+      for (int j = J0; j < 15; ++j)                                                    // NumFluxes.jl:78 (one-phase form)
+        emit(j, (s_r * Fa[j * T] - s_l * Fb[j * T]) * inv_ds + k_q * (b[j * T] - a[j * T]), 0.0, 0.0);
+    }
+  } else {
+    double acc[15];
+#pragma unroll
+    for (int j = 0; j < 15; ++j) acc[j] = 0.0;
+    if (MPH) path_integral<GEN, T>(eos, a, b, c_glob_x, c_glob_w, acc, bad);           // NumFluxes.jl:35-47
+#pragma unroll
+    for (int j = J0; j < 15; ++j) {
+      const double cons = 0.5 * (Fa[j * T] + Fb[j * T]) - 0.5 * lambda * (b[j * T] - a[j * T]);  // :30
+      const double d = (MPH && j != 1) ? 0.5 * acc[j] : 0.0;                                       // :50-51
+      emit(j, cons, d, d);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct StepArgs {
+  const double* Qin; double* Qout;
+  const double* lo_in; const double* hi_in; double* lo_out; double* hi_out;
+  unsigned long long* lam;   // [3][nprob] bit patterns of lambda_max (non-negative doubles order like u64)
+  double* tt;                // [3][nprob] time
+  long long* steps;          // [nprob]
+  int* status;
+  double* dt_hist; long long hist_k, hist_cap;   // dt_hist[prob*hist_cap + hist_k]
+  long long stride;
+  int ncells, nprob, tiles_per_prob;
+  int cur, nxt, clr;
+  double cfl, dx, t_end;
+  EosPair eos;
+};
+
+template <int T> constexpr size_t step_smem_bytes() { return sizeof(double) * (45 * T + 2 * T + 32); }
+
+template <int MODEL, int FLUX, bool GEN, int T>
+__global__ void __launch_bounds__(T) k_step(const StepArgs g) {
+  using MT = ModelTraits<MODEL>;
+  constexpr int NPH = MT::NPH, CPB = T / NPH, J0 = MT::J0;
+  extern __shared__ double smem[];
+  double* Rs = smem;            // records        [15][T]
+  double* Fs = Rs + 15 * T;     // physical flux  [15][T]
+  double* Hs = Fs + 15 * T;     // Q_hll, then the fluctuation handed to the left cell [15][T]
+  double* lo_s = Hs + 15 * T;   // [CPB]
+  double* hi_s = lo_s + T;      // [CPB]
+  double* red = hi_s + T;       // [T/32]
+
+  const int tid = threadIdx.x, l = tid / NPH, ph = tid % NPH;
+  const int prob = blockIdx.x / g.tiles_per_prob, tile = blockIdx.x % g.tiles_per_prob;
+  const int c = tile * (CPB - 2) + l;
+  const bool valid = c < g.ncells;
+  const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
+  const EosDev& eos = g.eos.e[ph];
+
+  const double lam_cur = __longlong_as_double((long long)g.lam[(size_t)g.cur * g.nprob + prob]);
+  const double t_cur = g.tt[(size_t)g.cur * g.nprob + prob];
+  const bool active = t_cur < g.t_end;                   // while t < T, main.jl:202
+  const double dt = g.cfl * g.dx / lam_cur;              // main.jl:212
+  const double dtdx = dt / g.dx;                         // main.jl:225
+  const double lambda = g.dx / dt;                       // main.jl:223
+  const double upd = (FLUX == FLUX_HLL) ? dtdx : 1.0 / lambda;  // main.jl:59 / :40
+
+  const bool own_interior = valid && l >= 1 && l <= CPB - 2 && c <= g.ncells - 2;
+  const bool own_frozen = valid && ((c == 0) || (c == g.ncells - 1));   // main.jl:219-220
+
+  // ---- load the tile ----------------------------------------------------------------------
+  if (MODEL == MODEL_MPH30) {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) Rs[j * T + tid] = __ldg(g.Qin + (size_t)(15 * ph + j) * g.stride + gi);
+  } else {
+#pragma unroll
+    for (int v = 0; v < 13; ++v) Rs[sp_slot(v) * T + tid] = __ldg(g.Qin + (size_t)v * g.stride + gi);
+  }
+  if (ph == 0) { lo_s[l] = __ldg(g.lo_in + gi); hi_s[l] = __ldg(g.hi_in + gi); }
+
+  if (!active) {  // this problem already reached t_end: carry the state through unchanged
+    if (own_interior || own_frozen) {
+      if (MODEL == MODEL_MPH30) {
+#pragma unroll
+        for (int j = 0; j < 15; ++j) g.Qout[(size_t)(15 * ph + j) * g.stride + gi] = Rs[j * T + tid];
+      } else {
+#pragma unroll
+        for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = Rs[sp_slot(v) * T + tid];
+      }
+      if (ph == 0) { g.lo_out[gi] = lo_s[l]; g.hi_out[gi] = hi_s[l]; }
+    }
+    if (tile == 0 && tid == 0) {
+      g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur;
+      g.lam[(size_t)g.nxt * g.nprob + prob] = (unsigned long long)__double_as_longlong(lam_cur);
+      g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
+    }
+    return;
+  }
+
+  int bad = 0;
+  // ---- per-cell state and physical flux (flux_mph, HyperelasticityMPh.jl:140-175) -----------
+  {
+    PhaseState st;
+    column_state<MODEL, GEN, T>(eos, Rs + tid, st);
+    if (valid) bad |= st.bad;
+    double A[9], f[15];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A[k] = Rs[(6 + k) * T + tid];
+    phase_flux(st, A, f);
+#pragma unroll
+    for (int j = J0; j < 15; ++j) Fs[j * T + tid] = f[j];
+  }
+  __syncthreads();
+
+  // ---- face between cell l-1 and cell l (hll / lxf, NumFluxes.jl) ---------------------------
+  const int tl = (l >= 1) ? tid - NPH : tid;   // halo threads evaluate a dummy face against themselves
+  double CR[15];                               // fluctuation kept by this (right) cell
+  {
+    int fbad = 0;
+    double* H = Hs + tid;
+    auto emit = [&](int j, double cons, double dm, double dp) {
+      H[j * T] = cons + dm;      // F_r - ... + NF_r of the left cell  (update_cell, main.jl:57-59)
+      CR[j] = dp - cons;         // - F_l + NF_l of this cell
+    };
+    face_eval<MODEL, FLUX, GEN, T>(eos, Rs + tl, Rs + tid, Fs + tl, Fs + tid, lo_s[(l >= 1) ? l - 1 : l], hi_s[l],
+                                   lambda, H, fbad, nullptr, emit);
+    if (valid && l >= 1) bad |= fbad;
+  }
+  __syncthreads();
+
+  // ---- conservative update (update_cell, main.jl:59 / :40) + wave bounds of the new state ----
+  double lamv = 0.0;
+  {
+    double qn[15];
+    const int tr = own_interior ? tid + NPH : tid;
+#pragma unroll
+    for (int j = J0; j < 15; ++j) {
+      const double q = Rs[j * T + tid];
+      qn[j] = own_interior ? q - upd * (Hs[j * T + tr] + CR[j]) : q;
+    }
+    if (own_interior) {
+      if (MODEL == MODEL_MPH30) {
+#pragma unroll
+        for (int j = 0; j < 15; ++j) g.Qout[(size_t)(15 * ph + j) * g.stride + gi] = qn[j];
+      } else {
+#pragma unroll
+        for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = qn[sp_slot(v)];
+      }
+    } else if (own_frozen) {
+      if (MODEL == MODEL_MPH30) {
+#pragma unroll
+        for (int j = 0; j < 15; ++j) g.Qout[(size_t)(15 * ph + j) * g.stride + gi] = qn[j];
+      } else {
+#pragma unroll
+        for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = qn[sp_slot(v)];
+      }
+    }
+    // CFL sweep of the next step (get_eigvals, main.jl:204-211) on the state just produced
+    PhaseState sn;
+    phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? qn[0] : 1.0, qn + 2, qn[5], qn + 6, sn);
+    const double cn = phase_cmax(eos, sn);
+    double lo_n = sn.u[0] - cn, hi_n = sn.u[0] + cn;
+    if (NPH == 2) {
+      lo_n = fmin(lo_n, __shfl_xor_sync(FULL, lo_n, 1));
+      hi_n = fmax(hi_n, __shfl_xor_sync(FULL, hi_n, 1));
+    }
+    if (own_interior) {
+      bad |= sn.bad;
+      if (ph == 0) { g.lo_out[gi] = lo_n; g.hi_out[gi] = hi_n; }
+      lamv = fmax(fabs(lo_n), fabs(hi_n));
+    } else if (own_frozen) {
+      if (ph == 0) { g.lo_out[gi] = lo_s[l]; g.hi_out[gi] = hi_s[l]; }
+      lamv = fmax(fabs(lo_s[l]), fabs(hi_s[l]));
+    }
+  }
+  // ---- block max of lambda, one atomic per block ---------------------------------------------
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lamv = fmax(lamv, __shfl_xor_sync(FULL, lamv, o));
+  if ((tid & 31) == 0) red[tid >> 5] = lamv;
+  bad = __any_sync(FULL, bad);
+  if (bad && (tid & 31) == 0) atomicOr(g.status, 1);
+  __syncthreads();
+  if (tid == 0) {
+    double mx = red[0];
+#pragma unroll
+    for (int w = 1; w < T / 32; ++w) mx = fmax(mx, red[w]);
+    atomicMax(g.lam + (size_t)g.nxt * g.nprob + prob, (unsigned long long)__double_as_longlong(mx));
+    if (tile == 0) {
+      g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur + dt;   // main.jl:214
+      g.steps[prob] += 1;                                   // main.jl:215
+      if (g.dt_hist && g.hist_k < g.hist_cap) g.dt_hist[(size_t)prob * g.hist_cap + g.hist_k] = dt;
+      g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CFL sweep on a resident state (main.jl:204-212): lo/hi per cell, lambda_max per problem, and
+// optionally the full get_eigvals output (6 per phase) in Julia layout (6*NPH, ncells*nprob).
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, bool GEN, int T>
+__global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, double* __restrict__ lo, double* __restrict__ hi,
+                                              unsigned long long* lam_slot, double* eig_full, int* status, long long stride,
+                                              int ncells, int nprob, int tiles_per_prob, const EosPair eosp) {
+  using MT = ModelTraits<MODEL>;
+  constexpr int NPH = MT::NPH, CPB = T / NPH;
+  __shared__ double red[T / 32];
+  const int tid = threadIdx.x, l = tid / NPH, ph = tid % NPH;
+  const int prob = blockIdx.x / tiles_per_prob, tile = blockIdx.x % tiles_per_prob;
+  const int c = tile * CPB + l;
+  const bool valid = c < ncells;
+  const long long gi = (long long)prob * ncells + (valid ? c : ncells - 1);
+  const EosDev& eos = eosp.e[ph];
+  double rec[15];
+  if (MODEL == MODEL_MPH30) {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) rec[j] = __ldg(Q + (size_t)(15 * ph + j) * stride + gi);
+  } else {
+    rec[0] = 1.0; rec[1] = 0.0;
+#pragma unroll
+    for (int v = 0; v < 13; ++v) rec[sp_slot(v)] = __ldg(Q + (size_t)v * stride + gi);
+  }
+  PhaseState st;
+  phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? rec[0] : 1.0, rec + 2, rec[5], rec + 6, st);
+  double S6[6], ev[3];
+  phase_acoustic_sym(eos, st, S6);
+  sym3_eigs(S6, ev);
+  const double cm = sqrt(fmax(fabs(ev[2]), fabs(ev[0])));
+  double lo_c = st.u[0] - cm, hi_c = st.u[0] + cm;
+  if (NPH == 2) {
+    lo_c = fmin(lo_c, __shfl_xor_sync(FULL, lo_c, 1));
+    hi_c = fmax(hi_c, __shfl_xor_sync(FULL, hi_c, 1));
+  }
+  double lamv = 0.0;
+  int bad = 0;
+  if (valid) {
+    bad = st.bad;
+    if (ph == 0) { lo[gi] = lo_c; hi[gi] = hi_c; }
+    lamv = fmax(fabs(lo_c), fabs(hi_c));
+    if (eig_full) {  // [u1 + c_k (ascending), u1 - c_k], HyperelasticityMPh.jl:263-265
+      double* e = eig_full + (size_t)gi * (6 * NPH) + 6 * ph;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double ck = sqrt(fabs(ev[k]));
+        e[k] = st.u[0] + ck;
+        e[3 + k] = st.u[0] - ck;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lamv = fmax(lamv, __shfl_xor_sync(FULL, lamv, o));
+  if ((tid & 31) == 0) red[tid >> 5] = lamv;
+  bad = __any_sync(FULL, bad);
+  if (bad && (tid & 31) == 0) atomicOr(status, 1);
+  __syncthreads();
+  if (tid == 0) {
+    double mx = red[0];
+#pragma unroll
+    for (int w = 1; w < T / 32; ++w) mx = fmax(mx, red[w]);
+    atomicMax(lam_slot + prob, (unsigned long long)__double_as_longlong(mx));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Julia layout (nvar, n) <-> structure of arrays [nvar][stride]; both sides coalesced through a
+// padded shared-memory tile of TC cells.
+// ------------------------------------------------------------------------------------------------
+template <int NVAR, int TC>
+__global__ void __launch_bounds__(256) k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, long long n, long long stride) {
+  __shared__ double tile[TC * NVAR + TC];  // [cell][var] with pad
+  const long long c0 = (long long)blockIdx.x * TC;
+  const int ncell = (int)((n - c0 < TC) ? (n - c0) : TC);
+  const int tot = ncell * NVAR;
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    const int cell = i / NVAR, v = i % NVAR;
+    tile[cell * (NVAR + 1) + v] = __ldg(aos + c0 * NVAR + i);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NVAR * TC; i += blockDim.x) {
+    const int v = i / TC, cell = i % TC;
+    if (cell < ncell) soa[(size_t)v * stride + c0 + cell] = tile[cell * (NVAR + 1) + v];
+  }
+}
+
+template <int NVAR, int TC>
+__global__ void __launch_bounds__(256) k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, long long n, long long stride) {
+  __shared__ double tile[TC * NVAR + TC];
+  const long long c0 = (long long)blockIdx.x * TC;
+  const int ncell = (int)((n - c0 < TC) ? (n - c0) : TC);
+  for (int i = threadIdx.x; i < NVAR * TC; i += blockDim.x) {
+    const int v = i / TC, cell = i % TC;
+    if (cell < ncell) tile[cell * (NVAR + 1) + v] = __ldg(soa + (size_t)v * stride + c0 + cell);
+  }
+  __syncthreads();
+  const int tot = ncell * NVAR;
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    const int cell = i / NVAR, v = i % NVAR;
+    aos[c0 * NVAR + i] = tile[cell * (NVAR + 1) + v];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stateless batches over Julia-layout arrays: literal drop-ins for the per-cell / per-face
+// reference functions.  One thread per (item, phase).
+// ------------------------------------------------------------------------------------------------
+enum { OP_CONS2PRIM = 0, OP_PRIM2CONS = 1, OP_FLUX = 2, OP_NONCONS = 3 };
+
+// energy(eos, S, finger(F)) for an arbitrary (rho-independent) F: prim2cons, HyperelasticityMPh.jl:75-76
+template <bool GEN>
+__device__ __forceinline__ double energy_of_F(const EosDev& eos, double S, const double* F) {
+  const double C11 = F[4] * F[8] - F[7] * F[5], C12 = F[7] * F[2] - F[1] * F[8], C13 = F[1] * F[5] - F[4] * F[2];
+  const double C21 = F[6] * F[5] - F[3] * F[8], C22 = F[0] * F[8] - F[6] * F[2], C23 = F[3] * F[2] - F[0] * F[5];
+  const double C31 = F[3] * F[7] - F[6] * F[4], C32 = F[6] * F[1] - F[0] * F[7], C33 = F[0] * F[4] - F[3] * F[1];
+  const double det = F[0] * C11 + F[3] * C12 + F[6] * C13;
+  const double id = 1.0 / det, k2 = id * id;   // G = C C^T / det^2,  I3 = 1/det^2
+  const double G0 = k2 * (C11 * C11 + C12 * C12 + C13 * C13), G1 = k2 * (C11 * C21 + C12 * C22 + C13 * C23);
+  const double G2 = k2 * (C11 * C31 + C12 * C32 + C13 * C33), G3 = k2 * (C21 * C21 + C22 * C22 + C23 * C23);
+  const double G4 = k2 * (C21 * C31 + C22 * C32 + C23 * C33), G5 = k2 * (C31 * C31 + C32 * C32 + C33 * C33);
+  const double I1 = G0 + G3 + G5;
+  const double I2 = 0.5 * (I1 * I1 - (G0 * G0 + G3 * G3 + G5 * G5 + 2.0 * (G1 * G1 + G2 * G2 + G4 * G4)));
+  const double r = fabs(id);  // I3^(1/2)
+  double rA, rB, rC;
+  if (GEN) { const double L = log(r); rA = exp(eos.ea * L); rB = exp(eos.eb * L); rC = exp(eos.eg * L); }
+  else { rA = r; rB = r * r * r; rC = r * r; }
+  const double U = eos.kA * (rA - 1.0) * (rA - 1.0) + eos.cvt0 * rC * (exp(S / eos.cv) - 1.0);   // EquationsOfState.jl:129-132
+  const double W = eos.hb * rB * (I1 * I1 * (1.0 / 3.0) - I2);                                     // :134
+  return U + W;
+}
+
+template <int MODEL, bool GEN, int OP>
+__global__ void __launch_bounds__(128) k_cellop(const double* __restrict__ in, double* __restrict__ out, long long n,
+                                                const EosPair eosp, int* status) {
+  using MT = ModelTraits<MODEL>;
+  constexpr int NPH = MT::NPH, NVAR = MT::NVAR;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / NPH;
+  const int ph = (int)(t % NPH);
+  const bool valid = i < n;
+  const long long ii = valid ? i : n - 1;
+  const EosDev& eos = eosp.e[ph];
+  const double* x = in + ii * NVAR + 15 * ph;   // SP: ph == 0
+  double* y = out + ii * NVAR + 15 * ph;
+  int bad = 0;
+  if (OP == OP_PRIM2CONS) {
+    if (MODEL == MODEL_MPH30) {   // HyperelasticityMPh.jl:66-87
+      const double frac = x[0], den = frac * x[1];
+      const double e_tot = energy_of_F<GEN>(eos, x[5], x + 6) + 0.5 * (x[2] * x[2] + x[3] * x[3] + x[4] * x[4]);
+      if (valid) {
+        y[0] = frac; y[1] = den;
+        y[2] = den * x[2]; y[3] = den * x[3]; y[4] = den * x[4];
+        y[5] = den * e_tot;
+        for (int k = 0; k < 9; ++k) y[6 + k] = den * x[6 + k];
+      }
+    } else {                      // Hyperelasticity.jl:70-93: P = [u(3), F(9 row-major), S]
+      double Fc[9];
+      for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) Fc[r + 3 * cc] = x[3 + 3 * r + cc];
+      const double det = Fc[0] * (Fc[4] * Fc[8] - Fc[7] * Fc[5]) + Fc[3] * (Fc[7] * Fc[2] - Fc[1] * Fc[8]) + Fc[6] * (Fc[1] * Fc[5] - Fc[4] * Fc[2]);
+      const double den = eos.rho0 / det;
+      const double e_tot = energy_of_F<GEN>(eos, x[12], Fc) + 0.5 * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+      if (valid) {
+        y[0] = den * x[0]; y[1] = den * x[1]; y[2] = den * x[2];
+        for (int k = 0; k < 9; ++k) y[3 + k] = den * x[3 + k];
+        y[12] = den * e_tot;
+      }
+    }
+    return;
+  }
+  double rec[15];
+  if (MODEL == MODEL_MPH30) { for (int j = 0; j < 15; ++j) rec[j] = x[j]; }
+  else { rec[0] = 1.0; rec[1] = 0.0; for (int v = 0; v < 13; ++v) rec[sp_slot(v)] = x[v]; }
+  PhaseState st;
+  phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? rec[0] : 1.0, rec + 2, rec[5], rec + 6, st);
+  bad = valid ? st.bad : 0;
+  if (OP == OP_CONS2PRIM) {       // HyperelasticityMPh.jl:106-133
+    const double S = eos.cv * log(st.Sp);   // EquationsOfState.jl:155
+    if (valid) {
+      if (MODEL == MODEL_MPH30) {
+        y[0] = rec[0]; y[1] = st.rho; y[2] = st.u[0]; y[3] = st.u[1]; y[4] = st.u[2]; y[5] = S;
+        for (int k = 0; k < 9; ++k) y[6 + k] = rec[6 + k] * st.inv_den;
+      } else {
+        y[0] = st.u[0]; y[1] = st.u[1]; y[2] = st.u[2];
+        for (int v = 3; v < 12; ++v) y[v] = rec[sp_slot(v)] * st.inv_den;
+        y[12] = S;
+      }
+    }
+  } else if (OP == OP_FLUX) {     // HyperelasticityMPh.jl:146-175 / Hyperelasticity.jl:99-114
+    double f[15];
+    phase_flux(st, rec + 6, f);
+    if (valid) {
+      if (MODEL == MODEL_MPH30) { for (int j = 0; j < 15; ++j) y[j] = f[j]; }
+      else { for (int v = 0; v < 13; ++v) y[v] = f[sp_slot(v)]; }
+    }
+  } else if (OP == OP_NONCONS) {  // HyperelasticityMPh.jl:178-250 (column 1 of each block)
+    double cc[15];
+    noncons_column(st, rec + 6, cc);
+    if (valid) for (int j = 0; j < 15; ++j) y[j] = cc[j];
+  }
+  bad = __any_sync(FULL, bad);
+  if (bad && (threadIdx.x & 31) == 0) atomicOr(status, 1);
+}
+
+// hll / lxf over a batch of faces (NumFluxes.jl:25-132).  eig_l / eig_r (6*NPH, n): the cached
+// get_eigvals of the adjacent cells; only their min / max are read (NumFluxes.jl:90-91).
+template <int MODEL, int FLUX, bool GEN, int T>
+__global__ void __launch_bounds__(T) k_faceop(const double* __restrict__ Ql, const double* __restrict__ Qr,
+                                              const double* __restrict__ eig_l, const double* __restrict__ eig_r,
+                                              double lambda, double* cons, double* dm, double* dp, double* s_out,
+                                              long long n, const EosPair eosp, int* status) {
+  using MT = ModelTraits<MODEL>;
+  constexpr int NPH = MT::NPH, NVAR = MT::NVAR, J0 = MT::J0;
+  extern __shared__ double smem[];
+  double* Ra = smem; double* Rb = Ra + 15 * T; double* Fa = Rb + 15 * T; double* Fb = Fa + 15 * T; double* Hs = Fb + 15 * T;
+  const int tid = threadIdx.x, ph = tid % NPH;
+  const long long i = ((long long)blockIdx.x * T + tid) / NPH;
+  const bool valid = i < n;
+  const long long ii = valid ? i : n - 1;
+  const EosDev& eos = eosp.e[ph];
+  int bad = 0;
+  for (int side = 0; side < 2; ++side) {
+    const double* x = (side ? Qr : Ql) + ii * NVAR + 15 * ph;
+    double* R = (side ? Rb : Ra) + tid;
+    double* F = (side ? Fb : Fa) + tid;
+    if (MODEL == MODEL_MPH30) { for (int j = 0; j < 15; ++j) R[j * T] = x[j]; }
+    else { R[0] = 1.0; R[T] = 0.0; for (int v = 0; v < 13; ++v) R[sp_slot(v) * T] = x[v]; }
+    PhaseState st;
+    column_state<MODEL, GEN, T>(eos, R, st);
+    bad |= st.bad;
+    double A[9], f[15];
+    for (int k = 0; k < 9; ++k) A[k] = R[(6 + k) * T];
+    phase_flux(st, A, f);
+    for (int j = 0; j < 15; ++j) F[j * T] = f[j];
+  }
+  double lo_l = 0.0, hi_r = 0.0;
+  if (FLUX == FLUX_HLL) {
+    const double* el = eig_l + ii * (6 * NPH);
+    const double* er = eig_r + ii * (6 * NPH);
+    lo_l = el[0]; hi_r = er[0];
+    for (int k = 1; k < 6 * NPH; ++k) { lo_l = fmin(lo_l, el[k]); hi_r = fmax(hi_r, er[k]); }
+  }
+  double sl_sr[2] = {0.0, 0.0};
+  const long long base = ii * NVAR + 15 * ph;
+  auto emit = [&](int j, double c_, double dm_, double dp_) {
+    if (!valid) return;
+    const int v = (MODEL == MODEL_MPH30) ? j : (j < 5 ? j - 2 : (j == 5 ? 12 : 3 + 3 * ((j - 6) % 3) + (j - 6) / 3));
+    if (cons) cons[base + v] = c_;
+    if (dm) dm[base + v] = dm_;
+    if (dp) dp[base + v] = dp_;
+  };
+  face_eval<MODEL, FLUX, GEN, T>(eos, Ra + tid, Rb + tid, Fa + tid, Fb + tid, lo_l, hi_r, lambda, Hs + tid, bad, sl_sr, emit);
+  if (valid && s_out && ph == 0) { s_out[2 * ii] = sl_sr[0]; s_out[2 * ii + 1] = sl_sr[1]; }
+  bad = __any_sync(FULL, valid ? bad : 0);
+  if (bad && (tid & 31) == 0) atomicOr(status, 1);
+  (void)J0;
+}
+
+// full get_eigvals over a Julia-layout batch (HyperelasticityMPh.jl:252-266)
+template <int MODEL, bool GEN>
+__global__ void __launch_bounds__(128) k_eigvals(const double* __restrict__ in, double* __restrict__ eig, long long n,
+                                                 const EosPair eosp, int* status) {
+  using MT = ModelTraits<MODEL>;
+  constexpr int NPH = MT::NPH, NVAR = MT::NVAR;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / NPH;
+  const int ph = (int)(t % NPH);
+  const bool valid = i < n;
+  const long long ii = valid ? i : n - 1;
+  const EosDev& eos = eosp.e[ph];
+  const double* x = in + ii * NVAR + 15 * ph;
+  double rec[15];
+  if (MODEL == MODEL_MPH30) { for (int j = 0; j < 15; ++j) rec[j] = x[j]; }
+  else { rec[0] = 1.0; rec[1] = 0.0; for (int v = 0; v < 13; ++v) rec[sp_slot(v)] = x[v]; }
+  PhaseState st;
+  phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? rec[0] : 1.0, rec + 2, rec[5], rec + 6, st);
+  double S6[6], ev[3];
+  phase_acoustic_sym(eos, st, S6);
+  sym3_eigs(S6, ev);
+  if (valid) {
+    double* e = eig + ii * (6 * NPH) + 6 * ph;
+    for (int k = 0; k < 3; ++k) { const double ck = sqrt(fabs(ev[k])); e[k] = st.u[0] + ck; e[3 + k] = st.u[0] - ck; }
+  }
+  int bad = __any_sync(FULL, valid ? st.bad : 0);
+  if (bad && (threadIdx.x & 31) == 0) atomicOr(status, 1);
+}
+
+}  // namespace hs

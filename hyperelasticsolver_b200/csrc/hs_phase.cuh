@@ -1,0 +1,245 @@
+// Per-phase constitutive math of the hot path, closed form, FP64, branch-light.
+//
+// One "phase record" is the 14 conserved numbers the physics reads
+//   alpha, m = alpha*rho*u (3), E = alpha*rho*E_tot, A = alpha*rho*F (9, column-major A[i+3j])
+// (Q[2] = alpha*rho is evolved but never read: HyperelasticityMPh.jl:110,148,183).  The
+// single-phase model is the same record with alpha == 1.
+//
+// What each routine replaces in the reference (all of it evaluated there through nested
+// ForwardDiff duals and heap-allocated 3x3 matrices):
+//   phase_state  : cons2prim HyperelasticityMPh.jl:106-133 (rho from det, :113-114),
+//                  finger Strains.jl:26-32, invariants Strains.jl:46-52,
+//                  entropy EquationsOfState.jl:139-156 (kept as S' = exp(S/cv), clamp included),
+//                  stress  EquationsOfState.jl:179-190 (row 1 only; closed form of the gradient),
+//                  temperature = derivative(energy, S) HyperelasticityMPh.jl:212
+//   phase_flux   : flux HyperelasticityMPh.jl:146-175
+//   phase_cmax2  : acoustic EquationsOfState.jl:223-246 for n = (1,0,0) (closed form of the
+//                  nested jacobian) + eigvals HyperelasticityMPh.jl:263 (largest |eigenvalue|)
+// Exact identities used (valid for every state, not only consistent ones):
+//   rho^2 = det(A)/(alpha^3 rho0)  =>  det F = rho0/rho,  I3 = det G = (rho/rho0)^2,
+//   so I3^(x/2) = (rho/rho0)^x: no pow/exp/log on the default exponents (alpha,beta,gamma)=(1,3,2),
+//   one log + three exp otherwise (GEN = true).
+// The header also compiles as plain C++ (tests/hostmath) so the closed forms can be checked
+// against the dual-number oracle on a machine without a GPU.  It is never a product CPU path.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define HS_HD __host__ __device__ __forceinline__
+#else
+#define HS_HD inline
+#endif
+
+namespace hs {
+
+// Barton2009 block exactly as the C ABI passes it (EquationsOfState.jl:71-85 field order) ...
+struct EosAbi {
+  double rho0, c0, cv, t0, b0, alpha, beta, gamma, b0sq, k0;
+};
+// ... and the derived constants the kernels use (computed once on the host).
+struct EosDev {
+  double rho0, inv_rho0, cvt0, inv_cvt0, t0, cv;
+  double b0sq, hb;        // b0^2, b0^2/2
+  double kA, kA1;         // k0/(2 alpha^2), k0/(2 alpha)
+  double ea, eb, eg;      // alpha, beta, gamma
+  double ha, hbeta, hg;   // alpha/2, beta/2, gamma/2
+};
+
+inline EosDev make_eos_dev(const EosAbi& e) {
+  EosDev d;
+  d.rho0 = e.rho0; d.inv_rho0 = 1.0 / e.rho0;
+  d.cvt0 = e.cv * e.t0; d.inv_cvt0 = 1.0 / (e.cv * e.t0);
+  d.t0 = e.t0; d.cv = e.cv;
+  d.b0sq = e.b0sq; d.hb = 0.5 * e.b0sq;
+  d.kA = 0.5 * e.k0 / (e.alpha * e.alpha); d.kA1 = 0.5 * e.k0 / e.alpha;
+  d.ea = e.alpha; d.eb = e.beta; d.eg = e.gamma;
+  d.ha = 0.5 * e.alpha; d.hbeta = 0.5 * e.beta; d.hg = 0.5 * e.gamma;
+  return d;
+}
+inline bool eos_is_default_exponents(const EosAbi& e) { return e.alpha == 1.0 && e.beta == 3.0 && e.gamma == 2.0; }
+
+HS_HD double hs_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+// Everything downstream needs from one phase record.  Symmetric tensors are stored as
+// [11,12,13,22,23,33].
+struct PhaseState {
+  double alpha, inv_alpha, rho, den, inv_den;
+  double u[3], Etot;
+  double G[6], G2r1[3];   // Finger tensor, row 1 of G^2
+  double I1, J;           // tr G ;  I1^2/3 - I2
+  double rB;              // (rho/rho0)^beta = I3^(beta/2)
+  double th;              // cv t0 I3^(gamma/2) (S' - 1)
+  double uc1, uc2;        // (rA-1) rA ;  (2 rA - 1) rA     (cold-compression pieces)
+  double Sp;              // S' = exp(S/cv), clamped at 1e-6 (EquationsOfState.jl:152-154)
+  double T;               // temperature de/dS = t0 I3^(gamma/2) S'
+  double a, e2, E3;       // M = a G - e2 G^2 + E3 I ,  sigma = -2 rho M
+  double sig1[3];         // row 1 of sigma (true stress of the phase, not alpha-weighted)
+  int bad;                // 1 where Julia would throw DomainError (sqrt of a negative) or NaN
+};
+
+template <bool GEN>
+HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double E, const double* A, PhaseState& s) {
+  // cofactors of A:  inv(A) = C^T / det A
+  const double C11 = A[4] * A[8] - A[7] * A[5], C12 = A[7] * A[2] - A[1] * A[8], C13 = A[1] * A[5] - A[4] * A[2];
+  const double C21 = A[6] * A[5] - A[3] * A[8], C22 = A[0] * A[8] - A[6] * A[2], C23 = A[3] * A[2] - A[0] * A[5];
+  const double C31 = A[3] * A[7] - A[6] * A[4], C32 = A[6] * A[1] - A[0] * A[7], C33 = A[0] * A[4] - A[3] * A[1];
+  // (A is column-major: A[i+3j]; C_ij = cofactor of A_ij.)  det by first row: A11 C11 + A12 C12 + A13 C13
+  const double detA = A[0] * C11 + A[3] * C12 + A[6] * C13;
+  const double ia = 1.0 / alpha;
+  const double x = detA * (ia * ia * ia) * eos.inv_rho0;      // det(A/alpha)/rho0 = rho^2
+  s.bad = !(x > 0.0);
+  const double rs = hs_rsqrt(x);                              // 1/rho
+  const double rho = x * rs;
+  s.alpha = alpha; s.inv_alpha = ia; s.rho = rho; s.den = alpha * rho; s.inv_den = ia * rs;
+  s.u[0] = m[0] * s.inv_den; s.u[1] = m[1] * s.inv_den; s.u[2] = m[2] * s.inv_den;
+  s.Etot = E * s.inv_den;
+  const double e_int = s.Etot - 0.5 * (s.u[0] * s.u[0] + s.u[1] * s.u[1] + s.u[2] * s.u[2]);
+  // G = (F F^T)^-1 = kappa^2 C C^T with kappa = den/det A = 1/(alpha^2 rho0 rho)
+  const double kap = rs * ia * ia * eos.inv_rho0, k2 = kap * kap;
+  s.G[0] = k2 * (C11 * C11 + C12 * C12 + C13 * C13);
+  s.G[1] = k2 * (C11 * C21 + C12 * C22 + C13 * C23);
+  s.G[2] = k2 * (C11 * C31 + C12 * C32 + C13 * C33);
+  s.G[3] = k2 * (C21 * C21 + C22 * C22 + C23 * C23);
+  s.G[4] = k2 * (C21 * C31 + C22 * C32 + C23 * C33);
+  s.G[5] = k2 * (C31 * C31 + C32 * C32 + C33 * C33);
+  const double* G = s.G;
+  s.I1 = G[0] + G[3] + G[5];
+  const double trG2 = G[0] * G[0] + G[3] * G[3] + G[5] * G[5] + 2.0 * (G[1] * G[1] + G[2] * G[2] + G[4] * G[4]);
+  const double I2 = 0.5 * (s.I1 * s.I1 - trG2);
+  s.J = s.I1 * s.I1 * (1.0 / 3.0) - I2;
+  // powers of I3 = r^2
+  const double r = rho * eos.inv_rho0;
+  double rA, rB, rC, irC;
+  if (GEN) {
+    const double L = log(r);
+    rA = exp(eos.ea * L); rB = exp(eos.eb * L); rC = exp(eos.eg * L); irC = 1.0 / rC;
+  } else {
+    const double ir = eos.rho0 * rs;
+    rA = r; rB = r * r * r; rC = r * r; irC = ir * ir;
+  }
+  s.rB = rB;
+  const double am1 = rA - 1.0;
+  s.uc1 = am1 * rA; s.uc2 = (2.0 * rA - 1.0) * rA;
+  const double W = eos.hb * rB * s.J;
+  double Sp = (e_int - W - eos.kA * am1 * am1) * eos.inv_cvt0 * irC + 1.0;
+  if (Sp != Sp) s.bad = 1;
+  if (Sp < 1e-6) Sp = 1e-6;
+  s.Sp = Sp;
+  s.th = eos.cvt0 * rC * (Sp - 1.0);
+  s.T = eos.t0 * rC * Sp;
+  // first derivatives of e(I1,I2,I3;S):  e1 = b0^2 rB I1/3, e2 = -b0^2 rB/2, E3 = e3*I3
+  const double e1 = eos.b0sq * rB * s.I1 * (1.0 / 3.0);
+  s.e2 = -eos.hb * rB;
+  s.E3 = eos.kA1 * s.uc1 + eos.hg * s.th + eos.hb * eos.hbeta * rB * s.J;
+  s.a = e1 + s.e2 * s.I1;
+  s.G2r1[0] = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
+  s.G2r1[1] = G[0] * G[1] + G[1] * G[3] + G[2] * G[4];
+  s.G2r1[2] = G[0] * G[2] + G[1] * G[4] + G[2] * G[5];
+  const double m2r = -2.0 * rho;
+  s.sig1[0] = m2r * (s.a * G[0] - s.e2 * s.G2r1[0] + s.E3);
+  s.sig1[1] = m2r * (s.a * G[1] - s.e2 * s.G2r1[1]);
+  s.sig1[2] = m2r * (s.a * G[2] - s.e2 * s.G2r1[2]);
+}
+
+// Physical x-flux of one phase in the 15-slot MPh order [0, den u1, mom(3), energy, A-block(9)].
+// HyperelasticityMPh.jl:168-172;  den*(u1 F_ij - u_i F_1j) == u1 A_ij - u_i A_1j.
+HS_HD void phase_flux(const PhaseState& s, const double* A, double* f) {
+  const double du1 = s.den * s.u[0];
+  const double as0 = s.alpha * s.sig1[0], as1 = s.alpha * s.sig1[1], as2 = s.alpha * s.sig1[2];
+  f[0] = 0.0;
+  f[1] = du1;
+  f[2] = du1 * s.u[0] - as0;
+  f[3] = du1 * s.u[1] - as1;
+  f[4] = du1 * s.u[2] - as2;
+  f[5] = du1 * s.Etot - (s.u[0] * as0 + s.u[1] * as1 + s.u[2] * as2);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double A1j = A[3 * j];
+    f[6 + 3 * j] = 0.0;  // u1 A_1j - u1 A_1j
+    f[7 + 3 * j] = s.u[0] * A[1 + 3 * j] - s.u[1] * A1j;
+    f[8 + 3 * j] = s.u[0] * A[2 + 3 * j] - s.u[2] * A1j;
+  }
+}
+
+// Eigenvalues of a symmetric 3x3 [11,12,13,22,23,33] by the trigonometric closed form,
+// ascending.  (The reference calls LAPACK on a symmetric-to-roundoff matrix.)
+HS_HD void sym3_eigs(const double* a, double* ev) {
+  const double q = (a[0] + a[3] + a[5]) * (1.0 / 3.0);
+  const double p1 = a[1] * a[1] + a[2] * a[2] + a[4] * a[4];
+  const double b0 = a[0] - q, b3 = a[3] - q, b5 = a[5] - q;
+  const double p2 = b0 * b0 + b3 * b3 + b5 * b5 + 2.0 * p1;
+  if (!(p2 > 0.0)) { ev[0] = ev[1] = ev[2] = q; return; }
+  const double p = sqrt(p2 * (1.0 / 6.0));
+  const double ip = 1.0 / p;
+  const double c0 = b0 * ip, c1 = a[1] * ip, c2 = a[2] * ip, c3 = b3 * ip, c4 = a[4] * ip, c5 = b5 * ip;
+  double r = 0.5 * (c0 * (c3 * c5 - c4 * c4) - c1 * (c1 * c5 - c4 * c2) + c2 * (c1 * c4 - c3 * c2));
+  r = fmin(1.0, fmax(-1.0, r));
+  const double phi = acos(r) * (1.0 / 3.0);
+  ev[2] = q + 2.0 * p * cos(phi);
+  ev[0] = q + 2.0 * p * cos(phi + 2.0943951023931954923);
+  ev[1] = 3.0 * q - ev[0] - ev[2];
+}
+HS_HD double sym3_max_abs_eig(const double* a) {
+  double ev[3];
+  sym3_eigs(a, ev);
+  return fmax(fabs(ev[2]), fabs(ev[0]));
+}
+
+// Symmetrised acoustic tensor for n = (1,0,0):
+//   Omega_ij = (1/rho) sum_l d sigma_1i / dF_jl F_1l, entropy held fixed (EquationsOfState.jl:223-246).
+// With dF = e_j (x) row1(F):  d rho = -rho d_1j,  dG = -(g_j e_1^T + e_1 g_j^T),
+// dI1 = -2 G_1j, dI2 = I1 dI1 + 2 (G^2)_1j, dI3/I3 = -2 d_1j  (SURVEY.md A.5); only G, G^2 and
+// the scalar energy derivatives enter -- F itself drops out.
+HS_HD void phase_acoustic_sym(const EosDev& eos, const PhaseState& s, double* S6) {
+  const double* G = s.G;
+  double G2[6];
+  G2[0] = s.G2r1[0]; G2[1] = s.G2r1[1]; G2[2] = s.G2r1[2];
+  G2[3] = G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
+  G2[4] = G[1] * G[2] + G[3] * G[4] + G[4] * G[5];
+  G2[5] = G[2] * G[2] + G[4] * G[4] + G[5] * G[5];
+  const int ix[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  const double M1[3] = {s.a * G[0] - s.e2 * G2[0] + s.E3, s.a * G[1] - s.e2 * G2[1], s.a * G[2] - s.e2 * G2[2]};
+  const double b3 = eos.b0sq * s.rB * (1.0 / 3.0);  // d e1 / d I1
+  const double e1 = b3 * s.I1;
+  const double dE3c = eos.kA1 * eos.ha * s.uc2 + eos.hg * eos.hg * s.th + eos.hb * eos.hbeta * eos.hbeta * s.rB * s.J;
+  double Om[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double d1j = (j == 0) ? 1.0 : 0.0;
+    const double d3 = -2.0 * d1j;  // dI3 / I3
+    const double dI1 = -2.0 * G[ix[0][j]];
+    const double dI2 = s.I1 * dI1 + 2.0 * G2[ix[0][j]];
+    const double dJ = (2.0 / 3.0) * s.I1 * dI1 - dI2;
+    const double de1 = b3 * dI1 + e1 * eos.hbeta * d3;
+    const double de2 = s.e2 * eos.hbeta * d3;
+    const double da = de1 + de2 * s.I1 + s.e2 * dI1;
+    const double dE3 = dE3c * d3 + eos.hb * eos.hbeta * s.rB * dJ;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double di1 = (i == 0) ? 1.0 : 0.0;
+      const double Gij = G[ix[i][j]];
+      const double dM = da * G[ix[0][i]] - s.a * (G[ix[0][j]] * di1 + Gij) - de2 * G2[ix[0][i]] +
+                        s.e2 * ((G[ix[0][j]] * G[ix[0][i]] + G2[ix[i][j]]) + (G2[ix[0][j]] * di1 + G[0] * Gij)) +
+                        dE3 * di1;
+      Om[i][j] = -2.0 * (dM - d1j * M1[i]);
+    }
+  }
+  S6[0] = Om[0][0]; S6[1] = 0.5 * (Om[0][1] + Om[1][0]); S6[2] = 0.5 * (Om[0][2] + Om[2][0]);
+  S6[3] = Om[1][1]; S6[4] = 0.5 * (Om[1][2] + Om[2][1]); S6[5] = Om[2][2];
+}
+
+// c_max = sqrt(max_k |eig_k(Omega)|): the only thing any consumer of get_eigvals keeps
+// (main.jl:210, NumFluxes.jl:90-91 take min / max / max|.| of u1 +- c_k).
+HS_HD double phase_cmax(const EosDev& eos, const PhaseState& s) {
+  double S6[6];
+  phase_acoustic_sym(eos, s, S6);
+  return sqrt(sym3_max_abs_eig(S6));
+}
+
+}  // namespace hs

@@ -1,0 +1,128 @@
+"""The time loop of main.jl:202-241 behind the C ABI: a device-resident solver object plus the
+host-side helpers of main.jl that do not touch physics (`initial_condition`, main.jl:99-106).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .testcases import riemann_grid
+
+__all__ = ["Solver", "initial_condition", "update_cell"]
+
+_FLUX = {"hll": L.HLL, "lxf": L.LXF, L.HLL: L.HLL, L.LXF: L.LXF}
+
+
+def initial_condition(Ql, Qr, nx):
+    """main.jl:99-106 -> (nx, nvar), byte-identical to Julia's (nvar, nx) column-major array."""
+    return riemann_grid(Ql, Qr, nx)
+
+
+class Solver:
+    """Owns the device copy of Q0 (structure-of-arrays, double-buffered) for `nprob` independent
+    problems of `ncells` cells.  One instance replaces the body of `while t < T` (main.jl:202-227).
+    """
+
+    def __init__(self, eos, ncells, nprob=1, model=L.MPH30, device=0):
+        self.model, self.nvar = model, L.NVAR[model]
+        self.ncells, self.nprob, self.device = int(ncells), int(nprob), int(device)
+        self._ctx = C.c_void_p()
+        self._eos = L.eos_array(eos, model)
+        L.check(L.lib().hs_create(C.byref(self._ctx), model, self._eos, L.NPHASE[model], self.ncells, self.nprob, self.device))
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            L.lib().hs_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- state --------------------------------------------------------------------------------
+    def _shape(self):
+        return (self.ncells, self.nvar) if self.nprob == 1 else (self.nprob, self.ncells, self.nvar)
+
+    def upload(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        if Q.size != self.nprob * self.ncells * self.nvar:
+            raise ValueError(f"expected {self._shape()} values, got {Q.shape}")
+        L.check(L.lib().hs_upload(self._ctx, Q.ctypes.data))
+        self.t = np.zeros(self.nprob)
+        self.steps = np.zeros(self.nprob, dtype=np.int64)
+        return self
+
+    def download(self, out=None):
+        Q = np.empty(self._shape()) if out is None else out
+        L.check(L.lib().hs_download(self._ctx, Q.ctypes.data))
+        return Q
+
+    def set_time(self, t, step=0):
+        """restart: main.jl:185-186"""
+        self.t[:] = t
+        self.steps[:] = step
+        L.check(L.lib().hs_set_time(self._ctx, float(t), int(step)))
+
+    # -- the loop -----------------------------------------------------------------------------
+    def wave_speeds(self, full=False):
+        """CFL sweep main.jl:204-212 -> lambda_max per problem (and get_eigvals of every cell)."""
+        lam = np.empty(self.nprob)
+        eig = np.empty(self._shape()[:-1] + (6 * L.NPHASE[self.model],)) if full else None
+        L.check(L.lib().hs_wave_speeds(self._ctx, eig.ctypes.data if full else None, lam.ctypes.data))
+        return (lam, eig) if full else lam
+
+    def step(self, flux="hll", cfl=0.6, dx=None):
+        """One iteration of main.jl:204-227; returns dt per problem."""
+        dx = 1.0 / self.ncells if dx is None else dx
+        dt = np.empty(self.nprob)
+        L.check(L.lib().hs_step(self._ctx, _FLUX[flux], float(cfl), float(dx), dt.ctypes.data))
+        self.t += dt          # main.jl:214
+        self.steps += 1       # main.jl:215
+        return dt
+
+    def advance(self, t_end, flux="hll", cfl=0.6, dx=None, max_steps=1 << 30, record_dt=False):
+        """`while t < T` (main.jl:202): device-resident until every problem has t >= t_end (no
+        clipping of the last step) or max_steps more steps were taken.  Updates self.t / self.steps;
+        returns the (nprob, max_steps) dt history if record_dt."""
+        dx = 1.0 / self.ncells if dx is None else dx
+        if record_dt and max_steps > (1 << 24):
+            raise ValueError("record_dt needs a finite max_steps")
+        hist = np.zeros((self.nprob, max_steps)) if record_dt else None
+        L.check(L.lib().hs_advance(self._ctx, _FLUX[flux], float(cfl), float(dx), float(t_end), int(max_steps),
+                                   self.t.ctypes.data, self.steps.ctypes.data, hist.ctypes.data if record_dt else None))
+        return hist
+
+    def step_host(self, Qin, Qout=None, flux="hll", cfl=0.6, dx=None):
+        """One step on host arrays (upload + step + download), the literal drop-in for one pass
+        of main.jl:204-227 with Q0 in host memory."""
+        dx = 1.0 / self.ncells if dx is None else dx
+        Qin = np.ascontiguousarray(Qin, dtype=np.float64)
+        Qout = np.empty_like(Qin) if Qout is None else Qout
+        dt = np.empty(self.nprob)
+        L.check(L.lib().hs_step_host(self._ctx, _FLUX[flux], float(cfl), float(dx), Qin.ctypes.data, Qout.ctypes.data, dt.ctypes.data))
+        return Qout, dt
+
+
+def update_cell(Q3, flux_num, eigvals_or_lambda, dtdx_or_eos, eos=None, device=0):
+    """main.jl:30-60, both methods, on one 3-cell stencil `Q3` of shape (3, nvar):
+      update_cell(Q3, lxf, lambda, eos)                  -> main.jl:30-41
+      update_cell(Q3, hll, eigvals[3], dtdx, eos)        -> main.jl:43-60
+    """
+    Q3 = np.asarray(Q3, dtype=np.float64)
+    Q_l, Q, Q_r = Q3[0], Q3[1], Q3[2]
+    if eos is None:   # LxF method
+        lam, eos = float(eigvals_or_lambda), dtdx_or_eos
+        F_l, _, NF_l = flux_num(eos, Q_l, Q, lam, device=device)
+        F_r, NF_r, _ = flux_num(eos, Q, Q_r, lam, device=device)
+        return Q - 1.0 / lam * ((F_r - F_l) + (NF_r + NF_l))
+    eig, dtdx = eigvals_or_lambda, float(dtdx_or_eos)
+    F_l, _, NF_l = flux_num(eos, Q_l, Q, eig[0:2], device=device)
+    F_r, NF_r, _ = flux_num(eos, Q, Q_r, eig[1:3], device=device)
+    return Q - dtdx * ((F_r - F_l) + (NF_r + NF_l))

@@ -1,0 +1,160 @@
+/*
+ * hyperelastic_b200.h -- C ABI of the B200-native finite-volume hot path of
+ * BlackSiberian/HyperelasticSolver (libhyperelastic_b200.so).
+ *
+ * The reference has no FFI: its "operator API" is a set of pure Julia functions on heap
+ * Vector{Float64}/Matrix{Float64}.  Every entry point below names the
+ * reference interface it replaces (file:line in the reference tree).  A Julia driver reaches
+ * them with `ccall` (julia/HyperelasticB200.jl); the Python package
+ * hyperelasticsolver_b200 binds the same symbols with ctypes.
+ *
+ * Conventions
+ *  - All host arrays are Float64, "Julia layout": an (nvar, n) column-major matrix, i.e. one
+ *    cell / face per contiguous record of nvar doubles -- exactly Q0::Array{Float64}(30, nx)
+ *    of main.jl:101.  The library transposes to structure-of-arrays on the device.
+ *  - model HS_MODEL_MPH30: 2 phases x [alpha, alpha*rho, alpha*rho*u(3), alpha*rho*E,
+ *    alpha*rho*F(9, column-major)] (HyperelasticityMPh.jl:80-84).  HS_MODEL_SP13:
+ *    [rho*u(3), rho*F(9, row-major), rho*E] (Hyperelasticity.jl:81-91).
+ *  - Every function returns an int status (HS_OK == 0).  HS_ERR_DOMAIN is returned where the
+ *    Julia code would throw DomainError (sqrt/log of a negative: HyperelasticityMPh.jl:114,
+ *    EquationsOfState.jl:129-134) or produce NaN; results are still written.
+ *  - There is no CPU fallback: without a CUDA device every call returns HS_ERR_CUDA.
+ *  - A context is used from one host thread at a time; calls return when results are valid.
+ */
+#ifndef HYPERELASTIC_B200_H
+#define HYPERELASTIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { HS_OK = 0, HS_ERR_ARG = 1, HS_ERR_CUDA = 2, HS_ERR_DOMAIN = 3, HS_ERR_NCCL = 4 };
+enum { HS_MODEL_SP13 = 0, HS_MODEL_MPH30 = 1 };
+enum { HS_FLUX_LXF = 0, HS_FLUX_HLL = 1 };
+
+/* Barton2009 -- EquationsOfState.jl:71-85, same field order (b0sq = b0^2, k0 = c0^2 - 4/3 b0^2,
+ * EquationsOfState.jl:111-112).  One block per phase (phases may differ, main.jl:133). */
+typedef struct hs_barton2009 {
+  double rho0, c0, cv, t0, b0, alpha, beta, gamma, b0sq, k0;
+} hs_barton2009_t;
+
+typedef struct hs_ctx hs_ctx_t;
+
+const char* hs_version(void);
+/* message of the last failure on this thread ("" if none) */
+const char* hs_last_error(void);
+/* number of CUDA devices visible (0 => every compute call fails with HS_ERR_CUDA) */
+int hs_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stateful solver: replaces the body of the `while t < T` loop, main.jl:202-227.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Allocate device state for `nprob` independent problems of `ncells` cells each on CUDA device
+ * `device`.  eos: nphase blocks (2 for MPH30, 1 for SP13). */
+int hs_create(hs_ctx_t** ctx, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells,
+              int64_t nprob, int device);
+int hs_destroy(hs_ctx_t* ctx);
+
+/* Q0 of main.jl:101,179: (nvar, ncells, nprob) column-major.  Upload also evaluates the
+ * per-cell wave speeds of the new state (the CFL sweep main.jl:204-211) and resets t, steps. */
+int hs_upload(hs_ctx_t* ctx, const double* Q);
+int hs_download(hs_ctx_t* ctx, double* Q);
+/* set / get the clock of every problem (restart: main.jl:185-186) */
+int hs_set_time(hs_ctx_t* ctx, double t, int64_t step);
+
+/* CFL sweep main.jl:204-212: lambda_max[nprob] = max_i max|eigvals_i|; eig (6*nphase, ncells,
+ * nprob) receives get_eigvals of every cell if not NULL (HyperelasticityMPh.jl:252-266,
+ * per phase [u1+c_k, u1-c_k], c_k ascending). */
+int hs_wave_speeds(hs_ctx_t* ctx, double* eig_or_null, double* lambda_max);
+
+/* One time step, main.jl:204-227: dt = cfl*dx/lambda_max, boundary cells frozen
+ * (main.jl:219-220), interior cells updated with update_cell (main.jl:30-60).
+ * dt_out[nprob] (may be NULL). */
+int hs_step(hs_ctx_t* ctx, int flux, double cfl, double dx, double* dt_out);
+
+/* Device-resident loop: steps until t >= t_end (no clipping of the last step, main.jl:202,214)
+ * or max_steps more steps were taken.  Per problem: t_io[nprob], step_io[nprob] in/out (NULL =
+ * keep the context's own clock), dt_hist (max_steps, nprob) column-major or NULL. */
+int hs_advance(hs_ctx_t* ctx, int flux, double cfl, double dx, double t_end, int64_t max_steps,
+               double* t_io, int64_t* step_io, double* dt_hist);
+
+/* One step on HOST arrays: upload Qin, step, download into Qout (may alias Qin).  This is the
+ * literal drop-in for one iteration of main.jl:202-227 with Q0 living in Julia memory;
+ * host<->device copies are pipelined against the kernels. */
+int hs_step_host(hs_ctx_t* ctx, int flux, double cfl, double dx, const double* Qin, double* Qout,
+                 double* dt_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Stateless batches: literal drop-ins for the per-cell / per-face Julia functions.
+ * n = number of cells (faces).  device = CUDA device ordinal.
+ * ------------------------------------------------------------------------------------------ */
+/* cons2prim_mph HyperelasticityMPh.jl:99-133 / prim2cons_mph :63-90.  SP13 primitives are
+ * [u(3), F(9 row-major), S] = the arguments of prim2cons, Hyperelasticity.jl:70. */
+int hs_cons2prim(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* P, int64_t n, int device);
+int hs_prim2cons(int model, const hs_barton2009_t* eos, int nphase, const double* P, double* Q, int64_t n, int device);
+/* flux_mph HyperelasticityMPh.jl:140-175 / flux Hyperelasticity.jl:99-114 */
+int hs_flux(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* F, int64_t n, int device);
+/* noncons_flux HyperelasticityMPh.jl:178-250.  col (30, n): column 1 of each 15x15 diagonal
+ * block (the only non-zero entries, :223-230).  Bdense (30, 30, n) gets the full matrix if not NULL. */
+int hs_noncons_flux(const hs_barton2009_t* eos, const double* Q, double* col, double* Bdense, int64_t n, int device);
+/* get_eigvals HyperelasticityMPh.jl:252-266 with n = (1,0,0): eig (6*nphase, n) */
+int hs_get_eigvals(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* eig, int64_t n, int device);
+/* hll NumFluxes.jl:70-132: Ql, Qr (30, n); eig_l, eig_r (12, n) = get_eigvals of the two cells
+ * (the `eigvals` argument, main.jl:56-57).  cons = zeros (NumFluxes.jl:82), dm = D^-, dp = D^+,
+ * s (2, n) = [s_l, s_r] (may be NULL).  For SP13 (nvar 13, eig 6 x n) cons is the conservative
+ * HLL flux of NumFluxes.jl:75-78 and dm = dp = 0. */
+int hs_hll(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, const double* Qr,
+           const double* eig_l, const double* eig_r, double* cons, double* dm, double* dp, double* s,
+           int64_t n, int device);
+/* lxf NumFluxes.jl:25-60 (lambda = dx/dt) */
+int hs_lxf(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, const double* Qr, double lambda,
+           double* cons, double* dm, double* dp, int64_t n, int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-pointer layer (structure-of-arrays, caller-owned device memory and stream): what the
+ * one-process-per-GPU driver uses so that halo exchange / allreduce (NCCL through
+ * torch.distributed) can be enqueued on the same stream between steps.
+ *   Q      : [nvar][stride] doubles, stride = ncells*nprob (cell index = prob*ncells + i)
+ *   lo, hi : [stride] cached per-cell wave bounds min/max over phases of u1 -+ c_max
+ *   scal   : HS_SCAL_DOUBLES(nprob) doubles of per-problem scalars (lambda_max x3 slots, t x3
+ *            slots, step count, status); opaque, zero-initialise, see hsd_scal_* helpers
+ * ------------------------------------------------------------------------------------------ */
+#define HS_SCAL_SLOTS 8
+#define HS_SCAL_DOUBLES(nprob) (HS_SCAL_SLOTS * (nprob) + 8)
+
+typedef struct hsd_problem {
+  int model, nphase, gen;   /* gen: 1 = generic exponents (exp/log path), 0 = (alpha,beta,gamma)=(1,3,2) */
+  int reserved;
+  int64_t ncells, nprob, stride;
+  double eos_dev[2][20];    /* derived EoS constants, passed to the kernels by value */
+} hsd_problem_t;
+
+/* fill a problem descriptor (host only, no device work) */
+int hsd_problem_init(hsd_problem_t* prob_out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob);
+/* AoS (nvar, n) <-> SoA [nvar][stride] on the device */
+int hsd_aos_to_soa(const hsd_problem_t* p, const double* aos_dev, double* soa_dev, void* stream);
+int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa_dev, double* aos_dev, void* stream);
+/* CFL sweep: fills lo, hi and lambda_max slot `slot` of scal (after zeroing it) */
+int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* lo, double* hi, double* scal, int slot, void* stream);
+/* one fused step n: reads Qin/lo_in/hi_in and slot n%3, writes Qout/lo_out/hi_out and slot (n+1)%3;
+ * if dt_hist != NULL the step's dt of problem p is stored at dt_hist[p*hist_cap + hist_k] */
+int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n,
+             const double* Qin, const double* lo_in, const double* hi_in, double* Qout, double* lo_out, double* hi_out,
+             double* scal, double* dt_hist, int64_t hist_k, int64_t hist_cap, void* stream);
+/* address (device pointer) of the lambda_max slot that step n WRITES, as doubles [nprob]:
+ * the buffer to all-reduce(max) across ranks between step n and n+1 */
+double* hsd_scal_lambda_next(double* scal, int64_t nprob, int64_t n);
+double* hsd_scal_lambda_cur(double* scal, int64_t nprob, int64_t n);
+double* hsd_scal_time(double* scal, int64_t nprob, int64_t n);     /* t slot READ by step n */
+double* hsd_scal_steps(double* scal, int64_t nprob);               /* int64 step counts */
+double* hsd_scal_status(double* scal, int64_t nprob);              /* int32 status word */
+/* number of kernels launched by this library in this process (for bench accounting) */
+int64_t hs_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPERELASTIC_B200_H */

@@ -1,0 +1,23 @@
+// Test harness only: compiles hs_phase.cuh as plain C++ so the closed forms the CUDA kernels
+// use can be compared with the dual-number oracle on a machine without a GPU.
+// Not part of the product; nothing in hyperelasticsolver_b200/ loads it.
+#include "../../hyperelasticsolver_b200/csrc/hs_phase.cuh"
+using namespace hs;
+extern "C" {
+// out: rho, u(3), Etot, Sp, T, sig1(3), G(6), cmax, flux(15), S6(6), bad
+void hm_phase(const double* eos_abi, int gen, double alpha, const double* m, double E, const double* A, double* out) {
+  EosDev e = make_eos_dev(*reinterpret_cast<const EosAbi*>(eos_abi));
+  PhaseState s;
+  if (gen) phase_state<true>(e, alpha, m, E, A, s); else phase_state<false>(e, alpha, m, E, A, s);
+  int k = 0;
+  out[k++] = s.rho; for (int i = 0; i < 3; ++i) out[k++] = s.u[i];
+  out[k++] = s.Etot; out[k++] = s.Sp; out[k++] = s.T;
+  for (int i = 0; i < 3; ++i) out[k++] = s.sig1[i];
+  for (int i = 0; i < 6; ++i) out[k++] = s.G[i];
+  out[k++] = phase_cmax(e, s);
+  phase_flux(s, A, out + k); k += 15;
+  phase_acoustic_sym(e, s, out + k); k += 6;
+  out[k++] = s.bad;
+}
+void hm_sym3_eigs(const double* a, double* ev) { sym3_eigs(a, ev); }
+}

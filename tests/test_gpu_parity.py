@@ -1,0 +1,200 @@
+"""GPU parity: the CUDA path (through the C ABI) against the dual-number CPU oracle on the same
+seeded inputs.  Tolerances follow BASELINE.json north_star: <= 1e-12 relative per step,
+<= 1e-9 after N steps, on conserved variables."""
+import numpy as np
+import pytest
+
+from util import random_mph_prims, random_sp_prims, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_OP = 1e-12     # one evaluation / one step
+TOL_RUN = 1e-9     # after N steps
+
+
+def _eos(hs, kind):
+    if kind == "default":
+        return (hs.Barton2009(), hs.Barton2009())
+    return (hs.Barton2009(), hs.Barton2009(_rho0=8.93, _c0=6.22, _cv=9.0e-4, _t0=300, _b0=3.16, _alpha=1, _beta=3.577, _gamma=2.088))
+
+
+def _oeos(oracle, kind):
+    if kind == "default":
+        return [oracle.barton2009(), oracle.barton2009()]
+    return [oracle.barton2009(), oracle.barton2009(c0=6.22, cv=9.0e-4, b0=3.16, beta=3.577, gamma=2.088)]
+
+
+@pytest.mark.parametrize("kind", ["default", "hetero"])
+def test_cell_functions_mph(gpu, oracle, kind):
+    hs = gpu
+    rng = np.random.default_rng(11)
+    P = random_mph_prims(rng, 257)
+    eos, oe = _eos(hs, kind), _oeos(oracle, kind)
+    Q = hs.prim2cons_mph(eos, P)
+    Qo, _ = oracle.prim2cons(oe, oracle.MPH30, P)
+    assert relerr(Q, Qo) < TOL_OP
+    P2 = hs.cons2prim_mph(eos, Qo)
+    P2o, _ = oracle.cons2prim(oe, oracle.MPH30, Qo)
+    assert relerr(P2, P2o) < 1e-11          # entropy = cv*log(S') amplifies roundoff of e_int by 1/(cv t0)
+    F = hs.flux_mph(eos, Qo)
+    Fo, _ = oracle.flux(oe, oracle.MPH30, Qo)
+    assert relerr(F, Fo) < TOL_OP
+    col = hs.noncons_flux(eos, Qo, dense=False)
+    colo, _ = oracle.noncons_cols(oe, Qo)
+    assert relerr(col, colo) < TOL_OP
+    B = hs.noncons_flux(eos, Qo[:3])
+    Bo = oracle.noncons_dense(oe, Qo[:3])
+    assert B.shape == (3, 30, 30) and relerr(B.reshape(3, -1), Bo.reshape(3, -1), per_var=False) < TOL_OP
+    eg = hs.get_eigvals(eos, Qo)
+    ego, _ = oracle.get_eigvals(oe, oracle.MPH30, Qo)
+    assert relerr(eg, ego, per_var=False) < TOL_OP
+
+
+def test_cell_functions_sp(gpu, oracle):
+    hs = gpu
+    rng = np.random.default_rng(12)
+    P = random_sp_prims(rng, 130)
+    eos = hs.Barton2009()
+    oe = [oracle.barton2009()]
+    Q = hs.hyperelasticity.prim2cons(eos, P)
+    Qo, _ = oracle.prim2cons(oe, oracle.SP13, P)
+    assert relerr(Q, Qo) < TOL_OP
+    F = hs.hyperelasticity.flux(eos, Qo)
+    Fo, _ = oracle.flux(oe, oracle.SP13, Qo)
+    assert relerr(F, Fo) < TOL_OP
+    P2 = hs.hyperelasticity.cons2prim(eos, Qo)
+    P2o, _ = oracle.cons2prim(oe, oracle.SP13, Qo)
+    assert relerr(P2, P2o) < 1e-11
+    eg = hs.hyperelasticity.get_eigvals(eos, Qo)
+    ego, _ = oracle.get_eigvals(oe, oracle.SP13, Qo)
+    assert relerr(eg, ego, per_var=False) < TOL_OP
+
+
+@pytest.mark.parametrize("kind", ["default", "hetero"])
+def test_hll_lxf_faces(gpu, oracle, kind):
+    hs = gpu
+    rng = np.random.default_rng(13)
+    eos, oe = _eos(hs, kind), _oeos(oracle, kind)
+    n = 65
+    Pl = random_mph_prims(rng, n, spread=0.03); Pr = random_mph_prims(rng, n, spread=0.03)
+    Ql, _ = oracle.prim2cons(oe, 1, Pl); Qr, _ = oracle.prim2cons(oe, 1, Pr)
+    el, _ = oracle.get_eigvals(oe, 1, Ql); er, _ = oracle.get_eigvals(oe, 1, Qr)
+    cons, dm, dp, s = hs.hll(eos, Ql, Qr, [el, er], return_speeds=True)
+    co, dmo, dpo, so, st = oracle.hll(oe, Ql, Qr, el, er)
+    assert st == 0
+    assert np.all(cons == 0.0)                       # NumFluxes.jl:82
+    assert relerr(s, so, per_var=False) < TOL_OP
+    assert relerr(dm, dmo) < TOL_OP and relerr(dp, dpo) < TOL_OP
+    lam = 11.0
+    cons, dm, dp = hs.lxf(eos, Ql, Qr, lam)
+    co, dmo, dpo, st = oracle.lxf(oe, Ql, Qr, lam)
+    assert relerr(cons, co) < TOL_OP and relerr(dm, dmo) < TOL_OP and relerr(dp, dpo) < TOL_OP
+    assert np.array_equal(dm, dp)                    # NumFluxes.jl:50-51
+
+
+def test_golden_face_b4(gpu, oracle):
+    """one HLL face of test case 6."""
+    hs = gpu
+    eos = (hs.Barton2009(), hs.Barton2009())
+    Ql, Qr = hs.initial_states(eos, 6)
+    eg = hs.get_eigvals(eos, np.stack([Ql, Qr]))
+    _, dm, dp, s = hs.hll(eos, Ql, Qr, [eg[0], eg[1]], return_speeds=True)
+    assert abs(s[0] - (-5.746359242338784)) < 1e-13 and abs(s[1] - 5.668441896578543) < 1e-13
+    ref_dm = [-2.2136008888027487, -20.265569210477256, -5.7654714850916102, 1.1735829960630739, 1.8326561339193024, 3.9389545409005038]
+    ref_dp16 = [-2.3511677908532080, -20.783870213302766, -9.5444778788371067, -11.105551423375545, -22.660677109939218, -48.102868115282782]
+    assert np.allclose(dm[:6], ref_dm, rtol=1e-12, atol=0)
+    assert np.allclose(dp[15:21], ref_dp16, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("flux", ["hll", "lxf"])
+@pytest.mark.parametrize("tc,kind", [(6, "default"), (5, "default"), (7, "hetero")])
+def test_run_mph_small(gpu, oracle, flux, tc, kind):
+    hs = gpu
+    eos, oe = _eos(hs, kind), _oeos(oracle, kind)
+    nx, nsteps = 200, 25
+    Ql, Qr = hs.initial_states(eos, tc)
+    Q0 = hs.initial_condition(Ql, Qr, nx)
+    fk = oracle.HLL if flux == "hll" else oracle.LXF
+    ref = oracle.run(oe, oracle.MPH30, fk, Q0, 0.6, 1.0 / nx, 1e9, nsteps, nthreads=8)
+    assert ref["status"] == 0
+    with hs.Solver(eos, nx) as sol:
+        sol.upload(Q0)
+        # one step
+        dt1 = sol.step(flux, 0.6, 1.0 / nx)
+        one = oracle.run(oe, oracle.MPH30, fk, Q0, 0.6, 1.0 / nx, 1e9, 1, nthreads=8)
+        assert abs(dt1[0] - one["dt"][0, 0]) <= 1e-13 * dt1[0]
+        assert relerr(sol.download(), one["Q"]) < TOL_OP
+        # N steps through the device-resident loop
+        sol.upload(Q0)
+        hist = sol.advance(1e9, flux, 0.6, 1.0 / nx, max_steps=nsteps, record_dt=True)
+        Q = sol.download()
+        assert sol.steps[0] == nsteps
+        assert np.allclose(hist[0], ref["dt"][0], rtol=1e-11, atol=0)
+        assert abs(sol.t[0] - ref["t"][0]) < 1e-11 * ref["t"][0]
+        assert relerr(Q, ref["Q"]) < TOL_RUN
+        # frozen boundary cells (main.jl:219-220)
+        assert np.array_equal(Q[0], Q0[0]) and np.array_equal(Q[-1], Q0[-1])
+
+
+def test_golden_run_b5(gpu):
+    """tc6, nx=16, 5 steps."""
+    hs = gpu
+    eos = (hs.Barton2009(), hs.Barton2009())
+    Ql, Qr = hs.initial_states(eos, 6)
+    with hs.Solver(eos, 16) as sol:
+        sol.upload(hs.initial_condition(Ql, Qr, 16))
+        hist = sol.advance(1e9, "hll", 0.6, 1 / 16, max_steps=5, record_dt=True)
+        Q = sol.download()
+    ref_dt = [0.006525871150502139, 0.006525871150502139, 0.006446700759844828, 0.005958085061464478, 0.005706267106528782]
+    assert np.allclose(hist[0], ref_dt, rtol=1e-12, atol=0)
+    assert np.allclose(Q[7, :6], [0.38297853292399647, 3.5431983793351409, 1.1321498895965438, 0.32995939011061942, 0.78173554155610159, 1.7603676372817543], rtol=1e-11)
+    assert np.allclose(Q[:, [0, 1, 15, 16, 20]].sum(0), [7.9024417665803668, 71.345306122448974, 8.0975582334196332, 72.507755102040832, 136.32929234855314], rtol=1e-12)
+
+
+@pytest.mark.parametrize("flux", ["hll", "lxf"])
+def test_run_sp_small(gpu, oracle, flux):
+    hs = gpu
+    eos = hs.Barton2009()
+    oe = [oracle.barton2009()]
+    nx, nsteps = 300, 30
+    Ql, Qr = hs.hyperelasticity.initial_states(eos, 1)
+    Q0 = hs.initial_condition(Ql, Qr, nx)
+    fk = oracle.HLL if flux == "hll" else oracle.LXF
+    ref = oracle.run(oe, oracle.SP13, fk, Q0, 0.6, 1.0 / nx, 1e9, nsteps, nthreads=8)
+    with hs.Solver(eos, nx, model=hs.SP13) as sol:
+        sol.upload(Q0)
+        hist = sol.advance(1e9, flux, 0.6, 1.0 / nx, max_steps=nsteps, record_dt=True)
+        Q = sol.download()
+    assert np.allclose(hist[0], ref["dt"][0], rtol=1e-11, atol=0)
+    assert relerr(Q, ref["Q"]) < TOL_RUN
+
+
+def test_ensemble_per_problem_dt(gpu, oracle):
+    """Independent problems with their own dt / t (BASELINE config 4 in miniature), including
+    problems that reach t_end at different step counts."""
+    hs = gpu
+    rng = np.random.default_rng(5)
+    eos = (hs.Barton2009(), hs.Barton2009()); oe = [oracle.barton2009()] * 2
+    nprob, nx = 6, 70
+    Pl = random_mph_prims(rng, nprob, spread=0.03); Pr = random_mph_prims(rng, nprob, spread=0.03)
+    Ql = hs.prim2cons_mph(eos, Pl); Qr = hs.prim2cons_mph(eos, Pr)
+    Q0 = np.stack([hs.initial_condition(Ql[i], Qr[i], nx) for i in range(nprob)])
+    t_end = 0.012
+    ref = oracle.run(oe, oracle.MPH30, oracle.HLL, Q0, 0.6, 1.0 / nx, t_end, 400, nthreads=8)
+    assert ref["status"] == 0 and len(set(ref["steps"].tolist())) > 1
+    with hs.Solver(eos, nx, nprob=nprob) as sol:
+        sol.upload(Q0)
+        sol.advance(t_end, "hll", 0.6, 1.0 / nx, max_steps=400)
+        Q = sol.download()
+        assert np.array_equal(sol.steps, ref["steps"])
+        assert np.allclose(sol.t, ref["t"], rtol=1e-11)
+    assert relerr(Q.reshape(-1, 30), ref["Q"].reshape(-1, 30)) < TOL_RUN
+
+
+def test_domain_error(gpu):
+    hs = gpu
+    eos = (hs.Barton2009(), hs.Barton2009())
+    Ql, _ = hs.initial_states(eos, 6)
+    bad = Ql.copy(); bad[6:15] *= -1.0       # det(F) < 0 -> sqrt(negative) in cons2prim (HyperelasticityMPh.jl:114)
+    with pytest.raises(hs.DomainError):
+        hs.cons2prim_mph(eos, bad)
