@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hyperelastic_b200.h declares;
+argument errors are reported; without a GPU compute calls fail loudly (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "hyperelastic_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(hsd?_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(hs):
+    from hyperelasticsolver_b200 import _lib as L
+    names = _declared_symbols()
+    assert len(names) >= 25
+    raw = C.CDLL(L.SO_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in the header but not exported"
+        assert n in L.SIGNATURES, f"{n} has no ctypes signature"
+    assert set(L.SIGNATURES) == set(names)
+
+
+def test_struct_layouts(hs):
+    from hyperelasticsolver_b200 import _lib as L
+    assert C.sizeof(L.Barton2009) == 80
+    e = L.Barton2009()
+    assert e.as_tuple() == (8.93, 4.6, 3.9e-4, 300.0, 2.1, 1.0, 3.0, 2.0, 2.1 ** 2, 4.6 ** 2 - (4 / 3) * 2.1 ** 2)
+    assert C.sizeof(L.HsdProblem) == 4 * 4 + 3 * 8 + 2 * 20 * 8
+
+
+def test_problem_init_and_arg_errors(hs):
+    from hyperelasticsolver_b200 import _lib as L
+    lib = L.lib()
+    p = L.HsdProblem()
+    eos2 = L.eos_array((hs.Barton2009(), hs.Barton2009()), L.MPH30)
+    assert lib.hsd_problem_init(C.byref(p), L.MPH30, eos2, 2, 1000, 1) == 0
+    assert (p.model, p.nphase, p.gen, p.ncells, p.nprob, p.stride) == (1, 2, 0, 1000, 1, 1000)
+    het = L.eos_array((hs.Barton2009(), hs.Barton2009(_beta=3.577, _gamma=2.088)), L.MPH30)
+    assert lib.hsd_problem_init(C.byref(p), L.MPH30, het, 2, 1000, 4) == 0 and p.gen == 1 and p.stride == 4000
+    assert lib.hsd_problem_init(C.byref(p), L.MPH30, eos2, 1, 1000, 1) == L.HS_ERR_ARG
+    assert lib.hsd_problem_init(C.byref(p), 7, eos2, 2, 1000, 1) == L.HS_ERR_ARG
+    assert lib.hsd_problem_init(C.byref(p), L.MPH30, eos2, 2, 2, 1) == L.HS_ERR_ARG
+    assert b"ncells" in lib.hs_last_error()
+    with pytest.raises(ValueError):
+        L.eos_array((hs.Barton2009(),), L.MPH30)
+
+
+def test_no_cpu_fallback(hs):
+    """On a machine without a GPU every compute entry point must fail with HS_ERR_CUDA."""
+    from hyperelasticsolver_b200 import _lib as L
+    if L.lib().hs_device_count() > 0:
+        pytest.skip("GPU present")
+    eos = (hs.Barton2009(), hs.Barton2009())
+    with pytest.raises(hs.HyperelasticError) as ei:
+        hs.cons2prim_mph(eos, np.ones(30))
+    assert ei.value.code == L.HS_ERR_CUDA
+    with pytest.raises(hs.HyperelasticError):
+        hs.Solver(eos, 100)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing in the product package may reference it."""
+    pkg = os.path.join(ROOT, "hyperelasticsolver_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src and "oracle/" not in src.replace("dual-number oracle", ""), f

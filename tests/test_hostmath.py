@@ -1,0 +1,81 @@
+"""CPU: the closed forms the CUDA kernels use (hs_phase.cuh, compiled here as plain C++ into a
+test-only harness) against the dual-number oracle.  This is a check OF the kernel math, not a
+CPU path of the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hm():
+    so = os.path.join(HERE, "hostmath", "libhostmath.so")
+    src = os.path.join(HERE, "hostmath", "hostmath.cpp")
+    hdr = os.path.join(HERE, "..", "hyperelasticsolver_b200", "csrc", "hs_phase.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.hm_phase.argtypes = [dp, C.c_int, C.c_double, dp, C.c_double, dp, dp]
+    lib.hm_sym3_eigs.argtypes = [dp, dp]
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("name,kw,gen", [("default", {}, 0), ("default-genericpath", {}, 1),
+                                         ("alt", dict(c0=6.22, cv=9.0e-4, b0=3.16, beta=3.577, gamma=2.088), 1)])
+def test_closed_forms_vs_dual_oracle(hm, oracle, name, kw, gen):
+    rng = np.random.default_rng(1)
+    eos = oracle.barton2009(**kw)
+    rel = lambda a, b, s=None: np.abs(np.asarray(a) - np.asarray(b)).max() / (np.abs(np.asarray(b)).max() if s is None else s)
+    for it in range(120):
+        alpha = rng.uniform(0.05, 0.95)
+        F = np.eye(3) + 0.1 * rng.uniform(-1, 1, (3, 3))
+        u = rng.uniform(-2, 2, 3); S = rng.uniform(0, 2e-3)
+        Pp = np.array([alpha, 8.9 / np.linalg.det(F), *u, S, *F.flatten(order="F")])
+        Q, _ = oracle.prim2cons([eos, eos], 1, np.concatenate([Pp, Pp]))
+        q = Q[:15]
+        out = np.zeros(64)
+        m = np.ascontiguousarray(q[2:5]); A = np.ascontiguousarray(q[6:15])
+        hm.hm_phase(_p(eos), gen, q[0], _p(m), q[5], _p(A), _p(out))
+        rho, uu, Sp, T, sig1, Gs, cmax, fl, S6, bad = out[0], out[1:4], out[5], out[6], out[7:10], out[10:16], out[16], out[17:32], out[32:38], out[38]
+        assert bad == 0
+        Po, _ = oracle.cons2prim([eos, eos], 1, Q); Po = Po[:15]
+        Fo, So = Po[6:15], Po[5]
+        Go = oracle.finger(Fo)
+        assert rel(rho, Po[1]) < 1e-14 and rel(uu, Po[2:5], 1.0) < 1e-14
+        assert rel(eos[2] * np.log(Sp), So, 1e-3) < 1e-12
+        assert rel(T, oracle.temperature(eos, So, Go)) < 1e-12
+        assert rel(Gs, Go[[0, 3, 6, 4, 7, 8]]) < 1e-13
+        sig = oracle.stress(eos, So, Fo)
+        assert rel(sig1, sig[[0, 3, 6]]) < 1e-12
+        fo, _ = oracle.flux([eos, eos], 1, Q)
+        assert rel(fl, fo[:15]) < 1e-12
+        ac = oracle.acoustic(eos, So, Fo)
+        assert rel(S6, [ac[0, 0], ac[0, 1], ac[0, 2], ac[1, 1], ac[1, 2], ac[2, 2]]) < 1e-12
+        eg, _ = oracle.get_eigvals([eos, eos], 1, Q)
+        assert rel(Po[2] + cmax, eg[0].max()) < 1e-13
+
+
+def test_sym3_eigs(hm):
+    rng = np.random.default_rng(3)
+    for it in range(200):
+        M = rng.normal(size=(3, 3)); M = M + M.T
+        if it % 10 == 0:  # degenerate pair
+            Qm, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            M = Qm @ np.diag([2.0, 2.0, 5.0]) @ Qm.T
+        a = np.array([M[0, 0], M[0, 1], M[0, 2], M[1, 1], M[1, 2], M[2, 2]])
+        ev = np.zeros(3)
+        hm.hm_sym3_eigs(_p(a), _p(ev))
+        ref = np.linalg.eigvalsh(M)
+        assert np.abs(ev - ref).max() < 5e-15 * max(1.0, np.abs(ref).max()) * 8
+    a = np.array([3.0, 0, 0, 3.0, 0, 3.0]); ev = np.zeros(3)
+    hm.hm_sym3_eigs(_p(a), _p(ev))
+    assert np.array_equal(ev, [3.0, 3.0, 3.0])

@@ -1,0 +1,148 @@
+"""CPU: pin the C++ oracle against (i) SURVEY.md Appendix B, (ii) the committed vectors of the
+independent torch-autograd restatement, (iii) physical anchors.  (The reference ships no golden
+vectors and Julia is unavailable -> "parity unpinned", see oracle/README.md.)"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from hyperelasticsolver_b200.testcases import mph_primitive_states, riemann_grid, sp_primitive_states
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def B():
+    return json.load(open(os.path.join(G, "survey_appendix_b.json")))
+
+
+def _states(oracle, tc):
+    Pl, Pr = mph_primitive_states(tc)
+    Q, st = oracle.prim2cons(None, oracle.MPH30, np.stack([Pl, Pr]))
+    assert st == 0
+    return Q[0], Q[1]
+
+
+def test_quadrature(oracle, B):
+    x, w = oracle.quadrature(False)
+    assert np.allclose(x, B["gl6_nodes"], rtol=0, atol=1e-16) and np.allclose(w, B["gl6_weights"], rtol=0, atol=1e-16)
+    x, w = oracle.quadrature(True)
+    assert np.allclose(x, B["lobatto6_nodes"], rtol=0, atol=2e-16) and np.allclose(w, B["lobatto6_weights"], rtol=0, atol=1e-16)
+    assert abs(w.sum() - 1) < 1e-15
+
+
+def test_tc6_states_and_speeds(oracle, B):
+    Ql, Qr = _states(oracle, 6)
+    assert np.allclose(Ql, B["tc6_Ql"], rtol=1e-15, atol=0)
+    assert np.allclose(Qr[:15], B["tc6_Qr_phase1"], rtol=4e-16, atol=0)
+    assert np.allclose(Qr[15:], B["tc6_Qr_phase2"], rtol=1e-15, atol=0)
+    P, _ = oracle.cons2prim(None, oracle.MPH30, Ql)
+    assert np.allclose(P[:15], B["tc6_cons2prim_Ql_phase1"], rtol=2e-15, atol=0)
+    eg, _ = oracle.get_eigvals(None, oracle.MPH30, np.stack([Ql, Qr]))
+    u1 = P[2]
+    assert np.allclose(np.sort(eg[0, :3] - u1)[::-1], B["tc6_c_left"], rtol=1e-14)
+    assert np.allclose(np.sort(eg[1, :3])[::-1], B["tc6_c_right"], rtol=1e-14)
+
+
+def test_lambda_max_all_cases(oracle, B):
+    for tc, (lam, dt) in B["lambda_max_dt_nx1000_cfl06"].items():
+        Ql, Qr = _states(oracle, int(tc))
+        l = oracle.lambda_max(None, oracle.MPH30, np.stack([Ql, Qr]))
+        assert abs(l - lam) < 1e-14 * lam
+        assert abs(0.6 * 1e-3 / l - dt) < 1e-14 * dt
+
+
+def test_hll_face(oracle, B):
+    Ql, Qr = _states(oracle, 6)
+    eg, _ = oracle.get_eigvals(None, oracle.MPH30, np.stack([Ql, Qr]))
+    cons, dm, dp, s, st = oracle.hll(None, Ql, Qr, eg[0], eg[1])
+    h = B["hll_face_tc6"]
+    assert st == 0 and np.all(cons == 0)
+    assert abs(s[0, 0] - h["s_l"]) < 1e-14 and abs(s[0, 1] - h["s_r"]) < 1e-13
+    for got, key in ((dm[0, :6], "dm_1_6"), (dm[0, 15:21], "dm_16_21"), (dp[0, :6], "dp_1_6"), (dp[0, 15:21], "dp_16_21")):
+        assert np.allclose(got, h[key], rtol=2e-14, atol=0)
+
+
+def test_small_run(oracle, B):
+    Ql, Qr = _states(oracle, 6)
+    r = oracle.run(None, oracle.MPH30, oracle.HLL, riemann_grid(Ql, Qr, 16), 0.6, 1 / 16, 1e9, 5)
+    g = B["run_tc6_nx16_5steps"]
+    assert np.allclose(r["dt"][0], g["dt"], rtol=1e-14, atol=0)
+    assert np.allclose(r["Q"][7, :6], g["cell8_Q_1_6"], rtol=1e-14) and np.allclose(r["Q"][8, :6], g["cell9_Q_1_6"], rtol=1e-14)
+    assert np.allclose(r["Q"][:, [0, 1, 15, 16, 20]].sum(0), g["colsum_Q1_Q2_Q16_Q17_Q21"], rtol=1e-14)
+    # literal mode (update_cell per cell: every face twice, main.jl:43-60) is bit-identical
+    r2 = oracle.run(None, oracle.MPH30, oracle.HLL, riemann_grid(Ql, Qr, 16), 0.6, 1 / 16, 1e9, 5, literal=True)
+    assert np.array_equal(r["Q"], r2["Q"])
+
+
+def test_against_pyoracle_vectors(oracle):
+    d = json.load(open(os.path.join(G, "pyoracle_vectors.json")))
+    rel = lambda a, b: np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max()
+    assert len(d["cases"]) >= 12
+    for c in d["cases"]:
+        eos = [np.array(b) for b in c["eos_blocks"]]
+        Q, _ = oracle.prim2cons(eos, 1, np.array(c["P"]))
+        assert rel(Q, c["Q"]) < 1e-14
+        Q = np.array(c["Q"])
+        assert rel(oracle.cons2prim(eos, 1, Q)[0], c["cons2prim"]) < 1e-13
+        assert rel(oracle.flux(eos, 1, Q)[0], c["flux"]) < 1e-13
+        assert rel(oracle.get_eigvals(eos, 1, Q)[0][0], c["eigvals"]) < 1e-13
+        assert rel(oracle.noncons_cols(eos, Q)[0], c["noncons_cols"]) < 1e-13
+        for p in range(2):  # asymmetry of the reference's acoustic tensor is roundoff only
+            ac = np.array(c["acoustic"][p])
+            assert np.abs(ac - ac.T).max() < 1e-14 * np.abs(ac).max()
+
+
+def test_physical_anchors(oracle):
+    """F = I, S = 0 -> zero stress, T = t0, speeds (b0, b0, c0)."""
+    for e in (oracle.barton2009(), oracle.barton2009(c0=6.22, cv=9.0e-4, b0=3.16, beta=3.577, gamma=2.088)):
+        I9 = np.eye(3).flatten()
+        assert np.abs(oracle.stress(e, 0.0, I9)).max() < 1e-12
+        assert abs(oracle.temperature(e, 0.0, I9) - e[3]) < 1e-10
+        ev = np.linalg.eigvalsh(oracle.acoustic(e, 0.0, I9))
+        assert np.allclose(np.sqrt(ev), [e[4], e[4], e[1]], rtol=1e-13)
+
+
+def test_prim_cons_roundtrip_and_identical_phases(oracle):
+    """prim2cons o cons2prim == id on Q; identical phases stay bit-identical (tc 1-5)."""
+    Ql, Qr = _states(oracle, 5)
+    P, _ = oracle.cons2prim(None, 1, Ql)
+    Q2, _ = oracle.prim2cons(None, 1, P)
+    m = np.ones(30, bool); m[[1, 16]] = False     # Q[2] is passive (quirk Q2): rho comes from det
+    assert np.allclose(Q2[m], Ql[m], rtol=1e-13)
+    r = oracle.run(None, 1, oracle.HLL, riemann_grid(Ql, Qr, 40), 0.6, 1 / 40, 1e9, 12)
+    assert np.array_equal(r["Q"][:, :15], r["Q"][:, 15:])
+    assert np.all(r["Q"][:, 0] == 0.5)
+
+
+def test_conservation_tc6(oracle):
+    """per-phase mass and mixture momentum/energy change only by the boundary-flux budget."""
+    Ql, Qr = _states(oracle, 6)
+    nx, n = 64, 10
+    Q0 = riemann_grid(Ql, Qr, nx)
+    r = oracle.run(None, 1, oracle.HLL, Q0, 0.6, 1 / nx, 1e9, n)
+    Q = r["Q"]; t = r["t"][0]
+    Fl, _ = oracle.flux(None, 1, Ql); Fr, _ = oracle.flux(None, 1, Qr)
+    interior = slice(1, nx - 1)   # boundary cells are frozen, interior obeys the conservation law
+    for cols in ([1], [16], [2, 17], [3, 18], [4, 19], [5, 20]):
+        tot0 = Q0[interior][:, cols].sum(); tot1 = Q[interior][:, cols].sum()
+        budget = -(t * nx) * (Fr[cols].sum() - Fl[cols].sum())
+        assert abs((tot1 - tot0) - budget) < 1e-10 * max(1.0, abs(tot0))
+
+
+def test_sp_matches_mph_identical_phases(oracle):
+    """MPh with two identical phases at alpha = 1/2 reduces to the one-phase model:
+    Q_mph[phase] = Q_SP / 2 (F column- vs row-major)."""
+    Pl, Pr = sp_primitive_states(1)
+    Qs, _ = oracle.prim2cons(None, oracle.SP13, np.stack([Pl, Pr]))
+    nx, n = 60, 20
+    rs = oracle.run(None, oracle.SP13, oracle.HLL, riemann_grid(Qs[0], Qs[1], nx), 0.6, 1 / nx, 1e9, n)
+    Ql, Qr = _states(oracle, 4)
+    rm = oracle.run(None, oracle.MPH30, oracle.HLL, riemann_grid(Ql, Qr, nx), 0.6, 1 / nx, 1e9, n)
+    assert np.allclose(rs["dt"][0], rm["dt"][0], rtol=1e-13)
+    Qm, Qsp = rm["Q"], rs["Q"]
+    assert np.allclose(2 * Qm[:, 2:5], Qsp[:, 0:3], rtol=0, atol=1e-12)
+    assert np.allclose(2 * Qm[:, 5], Qsp[:, 12], rtol=1e-12)
+    Fm = 2 * Qm[:, 6:15].reshape(nx, 3, 3).transpose(0, 2, 1).reshape(nx, 9)   # column-major -> row-major
+    assert np.allclose(Fm, Qsp[:, 3:12], rtol=0, atol=1e-12)
