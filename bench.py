@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s (FP64) of the finite-volume time step, BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of main.jl:204-227 (CFL dt + HLL update of every interior cell) over the
+synthetic Riemann-problem grid.  Default workload = BASELINE.json configs[1]: single-phase
+(13-variable) 1-D Riemann problem, 2^24 cells per GPU, HLL flux, cfl 0.6 (weak scaling: N GPUs
+carry one global grid of N*2^24 cells, slab-decomposed with halo exchange + allreduce(max)).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs in HBM), `e2e` =
+the same step through the host-buffer API with the H2D/D2H copies of the whole state inside the
+timed region, `roofline` = the fused step kernel against the measured HBM peak, `cpu_baseline`
+= the CPU oracle (a C++ restatement of the reference: Julia is not installed) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOADS = {
+    # name: (model, log2 cells per GPU or total, scaling, description)
+    "sp13_2p24": dict(model="sp13", cells=1 << 24, scaling="weak", desc="single-phase 13-var 1-D Riemann problem (Hyperelasticity.jl test case 1), 2^24 cells per GPU, HLL"),
+    "mph30_2p24": dict(model="mph30", cells=1 << 24, scaling="weak", desc="two-phase 30-var 1-D Riemann problem (HyperelasticityMPh.jl test case 6), 2^24 cells per GPU, HLL path-conservative"),
+    "sp13_2p28": dict(model="sp13", cells=1 << 28, scaling="strong", desc="single-phase 1-D Riemann problem, 2^28 cells total, slab-decomposed, HLL"),
+    "ensemble": dict(model="mph30", cells=4096, nprob=65536, scaling="strong", desc="65,536 independent two-phase Riemann problems x 4,096 cells, randomised states, per-problem dt"),
+    "ensemble_sp": dict(model="sp13", cells=4096, nprob=65536, scaling="strong", desc="65,536 independent single-phase Riemann problems x 4,096 cells, randomised states, per-problem dt"),
+}
+METRIC = "cell-updates/sec (FP64)"
+UNIT = "cell-updates/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.05)] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def riemann_states(H, model):
+    if model == "mph30":
+        eos = (H.Barton2009(), H.Barton2009())
+        Ql, Qr = H.initial_states(eos, 6)
+        return eos, H.MPH30, Ql, Qr
+    eos = H.Barton2009()
+    Ql, Qr = H.hyperelasticity.initial_states(eos, 1)
+    return eos, H.SP13, Ql, Qr
+
+
+def ensemble_states(H, model, p0, p1, seed=20261017):
+    """BASELINE config 4 generator: PCG64(20261017), per problem and side
+    alpha1~U[0.1,0.9], u~U[-1,1]^3, S~U[0,1e-3], F = I + 0.05 U[-1,1]^(3x3), nominal density 8.9."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nprob = p1
+    a = rng.uniform(0.1, 0.9, (nprob, 2)); u = rng.uniform(-1, 1, (nprob, 2, 3)); S = rng.uniform(0, 1e-3, (nprob, 2))
+    F = np.eye(3)[None, None] + 0.05 * rng.uniform(-1, 1, (nprob, 2, 3, 3))
+    a, u, S, F = a[p0:p1], u[p0:p1], S[p0:p1], F[p0:p1]
+    det = np.linalg.det(F)
+    if model == "mph30":
+        P = np.zeros((p1 - p0, 2, 30))
+        for ph, al in enumerate((a, 1 - a)):
+            o = 15 * ph
+            P[..., o] = al; P[..., o + 1] = 8.9 / det; P[..., o + 2:o + 5] = u; P[..., o + 5] = S
+            P[..., o + 6:o + 15] = F.transpose(0, 1, 3, 2).reshape(p1 - p0, 2, 9)   # column-major
+        eos = (H.Barton2009(), H.Barton2009())
+        Q = H.prim2cons_mph(eos, P.reshape(-1, 30)).reshape(p1 - p0, 2, 30)
+        return eos, H.MPH30, Q
+    P = np.concatenate([u, F.reshape(p1 - p0, 2, 9), S[..., None]], axis=-1)
+    eos = H.Barton2009()
+    Q = H.hyperelasticity.prim2cons(eos, P.reshape(-1, 13)).reshape(p1 - p0, 2, 13)
+    return eos, H.SP13, Q
+
+
+def cpu_oracle_rate(model, seconds, threads, literal=True):
+    """The CPU restatement of main.jl on the host cores, on a bounded sample of the workload:
+    a Riemann grid of `cells` cells around the interface for `steps` steps (~`seconds` of work)."""
+    import oracle as O
+    om = O.MPH30 if model == "mph30" else O.SP13
+    from hyperelasticsolver_b200.testcases import mph_primitive_states, riemann_grid, sp_primitive_states
+    eos = [O.barton2009()] * (2 if om == O.MPH30 else 1)
+    Pl, Pr = mph_primitive_states(6) if om == O.MPH30 else sp_primitive_states(1)
+    Qlr, _ = O.prim2cons(eos, om, np.stack([Pl, Pr]))
+    cells = 4096
+    t0 = time.perf_counter()
+    O.run(eos, om, O.HLL, riemann_grid(Qlr[0], Qlr[1], cells), 0.6, 1.0 / cells, 1e9, 1, nthreads=threads, literal=literal)
+    rate = cells / (time.perf_counter() - t0)
+    steps = 4
+    cells = int(min(1 << 20, max(4096, rate * seconds / steps)))
+    Q0 = riemann_grid(Qlr[0], Qlr[1], cells)
+    t0 = time.perf_counter()
+    r = O.run(eos, om, O.HLL, Q0, 0.6, 1.0 / cells, 1e9, steps, nthreads=threads, literal=literal)
+    dt = time.perf_counter() - t0
+    assert r["status"] == 0
+    return cells * steps / dt, f"{cells} cells x {steps} steps of the same Riemann problem, HLL, {'update_cell per cell (every face twice, as main.jl does)' if literal else 'each face once'}", dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm on the host cores.  Julia is not
+    installed in this image, so this is the C++ oracle restatement (kind 'port'), in literal mode
+    (update_cell per cell, Threads.@threads -> std::thread over all host cores)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as O
+    wl = WORKLOADS[args.workload]
+    threads = O.hardware_threads()
+    om = O.MPH30 if wl["model"] == "mph30" else O.SP13
+    from hyperelasticsolver_b200.testcases import mph_primitive_states, riemann_grid, sp_primitive_states
+    eos = [O.barton2009()] * (2 if om == O.MPH30 else 1)
+    Pl, Pr = mph_primitive_states(6) if om == O.MPH30 else sp_primitive_states(1)
+    Qlr, _ = O.prim2cons(eos, om, np.stack([Pl, Pr]))
+    # bounded sample: size the grid so that W+K steps take about two minutes at most
+    probe = 2048
+    t0 = time.perf_counter()
+    O.run(eos, om, O.HLL, riemann_grid(Qlr[0], Qlr[1], probe), 0.6, 1.0 / probe, 1e9, 1, nthreads=threads, literal=True)
+    rate = probe / (time.perf_counter() - t0)
+    cells = int(min(1 << 20, max(2048, rate * 90.0 / (args.steps + args.warmup))))
+    Q = riemann_grid(Qlr[0], Qlr[1], cells)
+    if args.warmup:
+        Q = O.run(eos, om, O.HLL, Q, 0.6, 1.0 / cells, 1e9, args.warmup, nthreads=threads, literal=True)["Q"]
+    t0 = time.perf_counter()
+    r = O.run(eos, om, O.HLL, Q, 0.6, 1.0 / cells, 1e9, args.steps, nthreads=threads, literal=True)
+    el = time.perf_counter() - t0
+    v = cells * args.steps / el
+    sample = f"{cells} cells x {args.steps} steps (bounded sample of the {wl['desc']}), update_cell per cell as main.jl:221-226"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": args.workload, "description": wl["desc"], "flux": "hll", "cfl": 0.6,
+                                        "note": "CPU restatement of main.jl (C++ dual-number oracle), not Julia: julia is not installed in this image"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import hyperelasticsolver_b200 as H
+    from hyperelasticsolver_b200 import _lib as L
+    from hyperelasticsolver_b200.slab import CudaKernels, EnsembleSolver, SlabSolver, slab_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    model = wl["model"]
+    nvar = 30 if model == "mph30" else 13
+    flux = L.HLL
+    ensemble = "nprob" in wl
+
+    # ---- build the synthetic state on the device (not timed) ------------------------------------
+    if ensemble:
+        nprob_g, ncells = wl["nprob"], wl["cells"]
+        p0, p1 = nprob_g * rank // world, nprob_g * (rank + 1) // world
+        eos, hmodel, Qlr = ensemble_states(H, model, p0, p1)
+        kern = CudaKernels(eos, hmodel, dev)
+        sol = EnsembleSolver(kern, ncells, nprob_g)
+        left = torch.arange(ncells, device=dev) < ncells / 2
+        Qlr_d = torch.as_tensor(Qlr, device=dev)
+        chunk = 2048
+        aos = torch.empty(sol.nprob * ncells, nvar, dtype=torch.float64, device=dev)
+        for c0 in range(0, sol.nprob, chunk):
+            q = Qlr_d[c0:c0 + chunk]
+            aos[c0 * ncells:(c0 + q.shape[0]) * ncells] = torch.where(left[None, :, None], q[:, None, 0, :], q[:, None, 1, :]).reshape(-1, nvar)
+        sol.set_local_device(aos)
+        del aos
+        n_units = nprob_g * ncells
+        local_cells = sol.nprob * ncells
+        dx = 1.0 / ncells
+        updated_local = sol.nprob * (ncells - 2)
+    else:
+        eos, hmodel, Ql, Qr = riemann_states(H, model)
+        n_global = wl["cells"] * (world if wl["scaling"] == "weak" else 1)
+        kern = CudaKernels(eos, hmodel, dev)
+        sol = SlabSolver(kern, n_global)
+        gidx = torch.arange(sol.lo_g, sol.hi_g, device=dev)
+        aos = torch.where((gidx < n_global / 2)[:, None], torch.as_tensor(Ql, device=dev)[None, :], torch.as_tensor(Qr, device=dev)[None, :]).contiguous()
+        sol.set_local_device(aos)
+        del aos, gidx
+        n_units = n_global
+        local_cells = sol.nloc
+        dx = 1.0 / n_global
+        updated_local = sol.nloc - 2
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(args.warmup):
+        sol.step(flux, 0.6, dx)
+    torch.cuda.synchronize(); barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.15)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = kern.launches()
+    torch.cuda.synchronize(); barrier()
+    tw0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        sol.step(flux, 0.6, dx, kernel_events=ev[i])
+    e1.record()
+    torch.cuda.synchronize()
+    tw1 = time.perf_counter()
+    barrier()
+    launches = kern.launches() - launches0
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    clocks = sampler.stop(tw0, tw1) if sampler else None
+    sol.check_status()
+    value = n_units * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the fused step kernel -----------------------------------------------------
+    peak, peak_src = measured_peaks()
+    alg_bytes = 2 * nvar * 8 * updated_local
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp)).get(args.workload)
+        if tj:
+            traffic = tj.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_step (fused flux + update + next-step wave bounds)", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_cell_update": 2 * nvar * 8, "cell_updates_per_launch": updated_local, "peak_source": peak_src,
+                "note": "the path is FP64-pipe bound, not HBM bound (DESIGN.md): see profiles/ for the measured DFMA peak and pipe utilisation"}
+
+    # ---- end to end through the host-buffer API ------------------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    nbytes_state = local_cells * nvar * 8
+    if not ensemble and world == 1:
+        # the reference-facing C-ABI call: hs_step_host on (pinned) host arrays
+        del sol
+        torch.cuda.empty_cache()
+        host_in = torch.empty(local_cells, nvar, dtype=torch.float64, pin_memory=True)
+        host_out = torch.empty(local_cells, nvar, dtype=torch.float64, pin_memory=True)
+        idx = torch.arange(local_cells)
+        host_in.copy_(torch.where((idx < local_cells / 2)[:, None], torch.as_tensor(Ql)[None, :], torch.as_tensor(Qr)[None, :]))
+        hin, hout = host_in.numpy(), host_out.numpy()
+        with H.Solver(eos, local_cells, model=hmodel, device=local) as s2:
+            s2.step_host(hin, hout, "hll", 0.6, dx)     # warm-up (allocations, first-touch)
+            l0 = kern.launches()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                s2.step_host(hin if i % 2 == 0 else hout, hout if i % 2 == 0 else hin, "hll", 0.6, dx)
+            e2e_t = time.perf_counter() - t0
+            e2e_launches = kern.launches() - l0
+        e2e_api = "hs_step_host (C ABI): upload Q0 + CFL sweep + fused step + download Q1, every step"
+    else:
+        host_in = torch.empty(local_cells, nvar, dtype=torch.float64, pin_memory=True)
+        host_out = torch.empty(local_cells, nvar, dtype=torch.float64, pin_memory=True)
+        host_in.copy_(torch.as_tensor(sol.local_aos_host()))
+        sol.step_host(host_in, host_out, flux, 0.6, dx)
+        torch.cuda.synchronize(); barrier()
+        l0 = kern.launches()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            sol.step_host(host_in if i % 2 == 0 else host_out, host_out if i % 2 == 0 else host_in, flux, 0.6, dx)
+        torch.cuda.synchronize()
+        e2e_t = time.perf_counter() - t0
+        barrier()
+        e2e_launches = kern.launches() - l0
+        if world > 1:
+            t = torch.tensor([e2e_t], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_t = float(t.item())
+        e2e_api = "SlabSolver/EnsembleSolver.step_host: pinned host slab -> device, CFL sweep (+allreduce), fused step, device -> host, every step"
+    e2e = {"value": n_units * e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": nbytes_state * world, "d2h_bytes_per_step": nbytes_state * world,
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_t / e2e_steps, "api": e2e_api, "gpu_launches": e2e_launches}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle as O
+        threads = O.hardware_threads()
+        v, sample, el = cpu_oracle_rate(model, args.cpu_seconds, threads, literal=True)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": el,
+               "note": "C++ restatement of main.jl (dual-number AD like ForwardDiff); Julia itself is not installed in this image"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": wl["desc"], "model": None, "flux": "hll", "cfl": 0.6,
+                       "cells_total": n_units, "cells_per_gpu": local_cells,
+                       "parallelism": ("ensemble partition, no collective" if ensemble else f"slab x{world}, halo send/recv + allreduce(max) per step"),
+                       "l2": f"state {nbytes_state / 1e9:.2f} GB per GPU per buffer >> 126 MB L2 (inputs larger than L2, no flush needed)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        out["config"].pop("model")
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sp13_2p24", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -157,8 +157,9 @@ int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* lo, double*
 
 int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
              const double* lo_in, const double* hi_in, double* Qout, double* lo_out, double* hi_out, double* scal,
-             double* dt_hist, int64_t hist_k, int64_t hist_cap, void* stream) {
+             double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, void* stream) {
   if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
+  if (ghost_mask < 0 || ghost_mask > 3) return fail(HS_ERR_ARG, "ghost_mask must be 0..3");
   StepArgs a;
   a.Qin = Qin; a.Qout = Qout; a.lo_in = lo_in; a.hi_in = hi_in; a.lo_out = lo_out; a.hi_out = hi_out;
   a.lam = scal_lam(scal); a.tt = scal_t(scal, p->nprob); a.steps = scal_steps(scal, p->nprob);
@@ -166,6 +167,7 @@ int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_e
   a.dt_hist = dt_hist; a.hist_k = hist_k; a.hist_cap = dt_hist ? hist_cap : 0;
   a.stride = p->stride; a.ncells = (int)p->ncells; a.nprob = (int)p->nprob;
   a.cur = (int)(n % 3); a.nxt = (int)((n + 1) % 3); a.clr = (int)((n + 2) % 3);
+  a.ghost = ghost_mask;
   a.cfl = cfl; a.dx = dx; a.t_end = t_end;
   a.eos = eos_pair(p);
   if (p->model == HS_MODEL_MPH30) {
@@ -177,6 +179,16 @@ int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_e
     a.tiles_per_prob = (int)((p->ncells - 2 + (CPB - 2) - 1) / (CPB - 2));
     return launch_step_m<MODEL_SP13, T>(flux, p->gen, a, (int64_t)a.tiles_per_prob * p->nprob, (cudaStream_t)stream);
   }
+}
+
+int hsd_halo(const hsd_problem_t* p, double* Q, double* lo, double* hi, double* left, double* right, int mask, int unpack, void* stream) {
+  if (p->nprob != 1) return fail(HS_ERR_ARG, "halo exchange applies to a single slab-decomposed grid");
+  if (!mask) return HS_OK;
+  const int nvar = p->model == HS_MODEL_MPH30 ? 30 : 13;
+  k_halo<<<2, 32, 0, (cudaStream_t)stream>>>(Q, lo, hi, left, right, p->stride, (int)p->ncells, nvar, mask, unpack);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
 }
 
 double* hsd_scal_lambda_next(double* scal, int64_t nprob, int64_t n) { return scal + ((n + 1) % 3) * nprob; }
@@ -318,7 +330,7 @@ int hs_wave_speeds(hs_ctx_t* c, double* eig, double* lambda_max) {
 static int enqueue_step(hs_ctx* c, int flux, double cfl, double dx, double t_end, double* hist, int64_t hist_k, int64_t hist_cap) {
   const int a = (int)(c->n & 1), b = a ^ 1;
   int rc = hsd_step(&c->prob, flux, cfl, dx, t_end, c->n, c->Q[a], c->lo[a], c->hi[a], c->Q[b], c->lo[b], c->hi[b], c->scal,
-                    hist, hist_k, hist_cap, c->stream);
+                    hist, hist_k, hist_cap, 0, c->stream);
   if (rc == HS_OK) c->n += 1;
   return rc;
 }

@@ -198,6 +198,7 @@ struct StepArgs {
   long long stride;
   int ncells, nprob, tiles_per_prob;
   int cur, nxt, clr;
+  int ghost;                 // bit 0 / 1: the first / last cell is a halo copy owned by a neighbouring slab
   double cfl, dx, t_end;
   EosPair eos;
 };
@@ -232,7 +233,9 @@ __global__ void __launch_bounds__(T) k_step(const StepArgs g) {
   const double upd = (FLUX == FLUX_HLL) ? dtdx : 1.0 / lambda;  // main.jl:59 / :40
 
   const bool own_interior = valid && l >= 1 && l <= CPB - 2 && c <= g.ncells - 2;
-  const bool own_frozen = valid && ((c == 0) || (c == g.ncells - 1));   // main.jl:219-220
+  // frozen physical boundary cells, main.jl:219-220 (halo cells of a slab are neither written nor
+  // counted in lambda_max: their owner does both)
+  const bool own_frozen = valid && ((c == 0 && !(g.ghost & 1)) || (c == g.ncells - 1 && !(g.ghost & 2)));
 
   // ---- load the tile ----------------------------------------------------------------------
   if (MODEL == MODEL_MPH30) {
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, doub
   phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? rec[0] : 1.0, rec + 2, rec[5], rec + 6, st);
   double S6[6], ev[3];
   phase_acoustic_sym(eos, st, S6);
-  sym3_eigs(S6, ev);
+  if (eig_full) sym3_eigs_jacobi(S6, ev); else sym3_eigs(S6, ev);
   const double cm = sqrt(fmax(fabs(ev[2]), fabs(ev[0])));
   double lo_c = st.u[0] - cm, hi_c = st.u[0] + cm;
   if (NPH == 2) {
@@ -463,6 +466,21 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(const double* __restrict__ s
     const int cell = i / NVAR, v = i % NVAR;
     aos[c0 * NVAR + i] = tile[cell * (NVAR + 1) + v];
   }
+}
+
+// Halo pack / unpack for the slab decomposition: buf = [Q(nvar), lo, hi] of one cell.
+// pack: first owned cell (index 1) -> to_left, last owned (ncells-2) -> to_right.
+// unpack: from_left -> cell 0, from_right -> cell ncells-1.   mask bit 0 / 1 = left / right neighbour exists.
+__global__ void k_halo(double* Q, double* lo, double* hi, double* left, double* right, long long stride, int ncells, int nvar,
+                       int mask, int unpack) {
+  const int v = threadIdx.x;
+  if (v >= nvar + 2) return;
+  const int side = blockIdx.x;   // 0 left, 1 right
+  if (!(mask & (1 << side))) return;
+  double* buf = side ? right : left;
+  const long long cell = unpack ? (side ? ncells - 1 : 0) : (side ? ncells - 2 : 1);
+  double* p = v < nvar ? Q + (size_t)v * stride + cell : (v == nvar ? lo + cell : hi + cell);
+  if (unpack) *p = buf[v]; else buf[v] = *p;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -639,7 +657,7 @@ __global__ void __launch_bounds__(128) k_eigvals(const double* __restrict__ in, 
   phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? rec[0] : 1.0, rec + 2, rec[5], rec + 6, st);
   double S6[6], ev[3];
   phase_acoustic_sym(eos, st, S6);
-  sym3_eigs(S6, ev);
+  sym3_eigs_jacobi(S6, ev);
   if (valid) {
     double* e = eig + ii * (6 * NPH) + 6 * ph;
     for (int k = 0; k < 3; ++k) { const double ck = sqrt(fabs(ev[k])); e[k] = st.u[0] + ck; e[3 + k] = st.u[0] - ck; }

@@ -185,6 +185,32 @@ HS_HD void sym3_eigs(const double* a, double* ev) {
   ev[0] = q + 2.0 * p * cos(phi + 2.0943951023931954923);
   ev[1] = 3.0 * q - ev[0] - ev[2];
 }
+// All three eigenvalues, robust for (near-)degenerate pairs: cyclic Jacobi, fixed 6 sweeps.
+// Used by the full get_eigvals API (the trigonometric form loses ~sqrt(eps) on a degenerate pair,
+// e.g. the two shear speeds at F = I); the hot path only needs the largest one, which the
+// trigonometric form delivers to full precision when it is simple.
+HS_HD void sym3_eigs_jacobi(const double* s6, double* ev) {
+  double a00 = s6[0], a01 = s6[1], a02 = s6[2], a11 = s6[3], a12 = s6[4], a22 = s6[5];
+#define HS_JROT(app, aqq, apq, apr, aqr)                                                  \
+  if (apq != 0.0) {                                                                      \
+    const double th = (aqq - app) / (2.0 * apq);                                         \
+    const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));        \
+    const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;                                 \
+    app -= t * apq; aqq += t * apq; apq = 0.0;                                            \
+    const double r1 = c * apr - sn * aqr, r2 = sn * apr + c * aqr;                        \
+    apr = r1; aqr = r2;                                                                   \
+  }
+#pragma unroll 1
+  for (int sweep = 0; sweep < 6; ++sweep) {
+    HS_JROT(a00, a11, a01, a02, a12)
+    HS_JROT(a00, a22, a02, a01, a12)
+    HS_JROT(a11, a22, a12, a01, a02)
+  }
+#undef HS_JROT
+  ev[0] = fmin(a00, fmin(a11, a22));
+  ev[1] = fmax(fmin(a00, a11), fmin(fmax(a00, a11), a22));   // median
+  ev[2] = fmax(a00, fmax(a11, a22));
+}
 HS_HD double sym3_max_abs_eig(const double* a) {
   double ev[3];
   sym3_eigs(a, ev);

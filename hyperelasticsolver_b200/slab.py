@@ -1,0 +1,325 @@
+"""Multi-GPU driver, one process per GPU (torch.distributed): slab domain decomposition of one
+large 1-D grid with a one-cell halo, and partitioning of ensembles of independent problems.
+
+The reference has no distributed layer (its only parallelism is `Threads.@threads` over cells,
+main.jl:206,221); this is the B200 replacement of those two loops for grids that span GPUs.
+torch is plumbing only: device memory, the CUDA stream, and NCCL through torch.distributed.
+All arithmetic runs in libhyperelastic_b200.so through the device-pointer layer of the C ABI.
+
+Per step and per rank:
+    hsd_step                         fused kernel (reads lambda_max slot n%3, writes slot (n+1)%3)
+    halo exchange                    first / last owned cell (nvar + 2 doubles) to the neighbours
+    all_reduce(MAX) of slot (n+1)%3  -> dt of the next step is bit-identical on all ranks and
+                                        identical to the single-GPU run (max is exact)
+Both collectives are enqueued on the same stream as the kernels: no host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+__all__ = ["slab_bounds", "CudaKernels", "SlabSolver", "EnsembleSolver"]
+
+
+def slab_bounds(n_global: int, world: int, rank: int):
+    """Owned global cells [a, b) of `rank`, and the local array range [lo, hi) = owned cells plus
+    one halo cell on each side that has a neighbour.  The physical boundary cells (global 0 and
+    n-1, frozen by main.jl:219-220) are owned by the first / last rank and are the first / last
+    local cell there."""
+    a = n_global * rank // world
+    b = n_global * (rank + 1) // world
+    lo = a - (1 if rank > 0 else 0)
+    hi = b + (1 if rank < world - 1 else 0)
+    return a, b, lo, hi
+
+
+class CudaKernels:
+    """The product kernels behind the device-pointer ABI (hsd_*), on torch's current stream."""
+
+    def __init__(self, eos, model, device):
+        self.model = model
+        self.nvar = L.NVAR[model]
+        self.device = torch.device(device)
+        self._eos = L.eos_array(eos, model)
+        self._lib = L.lib()
+        if self._lib.hs_device_count() <= 0:
+            raise L.HyperelasticError(L.HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback")
+
+    def problem(self, ncells, nprob=1):
+        p = L.HsdProblem()
+        L.check(self._lib.hsd_problem_init(C.byref(p), self.model, self._eos, L.NPHASE[self.model], ncells, nprob))
+        return p
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64, device=self.device)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float64, device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def aos_to_soa(self, prob, aos, soa):
+        L.check(self._lib.hsd_aos_to_soa(C.byref(prob), aos.data_ptr(), soa.data_ptr(), self._stream()))
+
+    def soa_to_aos(self, prob, soa, aos):
+        L.check(self._lib.hsd_soa_to_aos(C.byref(prob), soa.data_ptr(), aos.data_ptr(), self._stream()))
+
+    def wave_bounds(self, prob, Q, lo, hi, scal, slot):
+        L.check(self._lib.hsd_wave_bounds(C.byref(prob), Q.data_ptr(), lo.data_ptr(), hi.data_ptr(), scal.data_ptr(), slot, self._stream()))
+
+    def step(self, prob, flux, cfl, dx, t_end, n, Qin, lo_in, hi_in, Qout, lo_out, hi_out, scal, ghost_mask, dt_hist=None, hist_k=0, hist_cap=0):
+        L.check(self._lib.hsd_step(C.byref(prob), flux, cfl, dx, t_end, n, Qin.data_ptr(), lo_in.data_ptr(), hi_in.data_ptr(),
+                                   Qout.data_ptr(), lo_out.data_ptr(), hi_out.data_ptr(), scal.data_ptr(),
+                                   dt_hist.data_ptr() if dt_hist is not None else None, hist_k, hist_cap, ghost_mask, self._stream()))
+
+    def halo(self, prob, Q, lo, hi, left, right, mask, unpack):
+        L.check(self._lib.hsd_halo(C.byref(prob), Q.data_ptr(), lo.data_ptr(), hi.data_ptr(), left.data_ptr(), right.data_ptr(),
+                                   mask, int(unpack), self._stream()))
+
+    def launches(self):
+        return int(self._lib.hs_kernel_launch_count())
+
+
+def scal_size(nprob):
+    return L.HS_SCAL_SLOTS * nprob + 8
+
+
+class _Base:
+    def _views(self):
+        np_ = self.nprob
+        s = self.scal
+        self._lam = [s[k * np_:(k + 1) * np_] for k in range(3)]          # lambda_max slots
+        self._t = [s[3 * np_ + k * np_:3 * np_ + (k + 1) * np_] for k in range(3)]
+        self._steps = s[6 * np_:7 * np_].view(torch.int64)
+        self._status = s[L.HS_SCAL_SLOTS * np_:L.HS_SCAL_SLOTS * np_ + 1].view(torch.int32)
+
+    @property
+    def t(self):
+        return self._t[self.n % 3].cpu().numpy().copy()
+
+    @property
+    def steps(self):
+        return self._steps.cpu().numpy().copy()
+
+    @property
+    def lambda_max(self):
+        return self._lam[self.n % 3].cpu().numpy().copy()
+
+    def check_status(self):
+        if int(self._status.cpu()[0]) != 0:
+            raise L.DomainError(L.HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError")
+
+
+class SlabSolver(_Base):
+    """One global grid of `n_global` cells split into contiguous slabs, one per rank."""
+
+    def __init__(self, kernels, n_global, group=None):
+        self.k = kernels
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_global = int(n_global)
+        self.nvar = kernels.nvar
+        self.nprob = 1
+        self.a, self.b, self.lo_g, self.hi_g = slab_bounds(self.n_global, self.world, self.rank)
+        self.nloc = self.hi_g - self.lo_g
+        if self.nloc < 3:
+            raise ValueError("slab too small: every rank needs at least 3 local cells")
+        self.ghost_mask = (1 if self.rank > 0 else 0) | (2 if self.rank < self.world - 1 else 0)
+        self.prob = kernels.problem(self.nloc, 1)
+        self.Q = [kernels.empty(self.nvar, self.nloc) for _ in range(2)]
+        self.lo = [kernels.empty(self.nloc) for _ in range(2)]
+        self.hi = [kernels.empty(self.nloc) for _ in range(2)]
+        self.scal = kernels.zeros(scal_size(1))
+        self._views()
+        self.n = 0
+        w = self.nvar + 2
+        self._send = [kernels.empty(w), kernels.empty(w)]   # to left, to right
+        self._recv = [kernels.empty(w), kernels.empty(w)]   # from left, from right
+
+    # -- state ----------------------------------------------------------------------------------
+    def set_local(self, Q_local):
+        """Q_local: (nloc, nvar) Julia-layout rows of global cells [lo_g, hi_g) (halo included)."""
+        aos = torch.as_tensor(np.ascontiguousarray(Q_local, dtype=np.float64)).to(self.k.device)
+        self.set_local_device(aos)
+
+    def set_local_device(self, aos, check=True):
+        """aos: device tensor (nloc, nvar)."""
+        assert tuple(aos.shape) == (self.nloc, self.nvar)
+        self.scal.zero_()
+        self.n = 0
+        self.k.aos_to_soa(self.prob, aos, self.Q[0])
+        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self._allreduce_lambda(0)
+        if check:
+            self.check_status()
+
+    def local_aos_host(self):
+        """(nloc, nvar) host copy of the local slab, halo cells included."""
+        aos = self.k.empty(self.nloc, self.nvar)
+        self.k.soa_to_aos(self.prob, self.Q[self.n & 1], aos)
+        return aos.cpu().numpy()
+
+    def step_host(self, host_in, host_out, flux=L.HLL, cfl=0.6, dx=None):
+        """One step on host slabs (pinned torch tensors (nloc, nvar)): H2D, CFL sweep (+ allreduce),
+        fused step, halo, D2H -- the multi-GPU counterpart of the C ABI's hs_step_host."""
+        if not hasattr(self, "_stage"):
+            self._stage = self.k.empty(self.nloc, self.nvar)
+        self._stage.copy_(host_in, non_blocking=True)
+        self.set_local_device(self._stage, check=False)
+        self.step(flux, cfl, dx)
+        self.k.soa_to_aos(self.prob, self.Q[self.n & 1], self._stage)
+        host_out.copy_(self._stage, non_blocking=True)
+        torch.cuda.current_stream(self.k.device).synchronize()
+
+    def set_from_global(self, Q_global):
+        self.set_local(np.asarray(Q_global)[self.lo_g:self.hi_g])
+
+    def owned(self):
+        """(a, b, Q_owned (b-a, nvar)) of the cells this rank owns."""
+        aos = self.k.empty(self.nloc, self.nvar)
+        self.k.soa_to_aos(self.prob, self.Q[self.n & 1], aos)
+        off = self.a - self.lo_g
+        return self.a, self.b, aos[off:off + (self.b - self.a)].cpu().numpy()
+
+    def gather(self):
+        """Global (n_global, nvar) array on every rank (test / IO helper; not on the hot path)."""
+        a, b, mine = self.owned()
+        if self.world == 1:
+            return mine
+        parts = [None] * self.world
+        dist.all_gather_object(parts, (a, b, mine), group=self.group)
+        out = np.empty((self.n_global, self.nvar))
+        for (pa, pb, q) in parts:
+            out[pa:pb] = q
+        return out
+
+    # -- communication ----------------------------------------------------------------------------
+    def _allreduce_lambda(self, slot):
+        if self.world > 1:
+            dist.all_reduce(self._lam[slot], op=dist.ReduceOp.MAX, group=self.group)
+
+    def _halo_exchange(self, buf):
+        if self.world == 1:
+            return
+        Q, lo, hi = self.Q[buf], self.lo[buf], self.hi[buf]
+        self.k.halo(self.prob, Q, lo, hi, self._send[0], self._send[1], self.ghost_mask, False)
+        ops = []
+        if self.rank > 0:
+            ops += [dist.P2POp(dist.isend, self._send[0], self.rank - 1, self.group), dist.P2POp(dist.irecv, self._recv[0], self.rank - 1, self.group)]
+        if self.rank < self.world - 1:
+            ops += [dist.P2POp(dist.isend, self._send[1], self.rank + 1, self.group), dist.P2POp(dist.irecv, self._recv[1], self.rank + 1, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        self.k.halo(self.prob, Q, lo, hi, self._recv[0], self._recv[1], self.ghost_mask, True)
+
+    # -- the loop -------------------------------------------------------------------------------
+    def step(self, flux=L.HLL, cfl=0.6, dx=None, t_end=1.0e300, kernel_events=None):
+        dx = 1.0 / self.n_global if dx is None else dx
+        a, b = self.n & 1, (self.n & 1) ^ 1
+        if kernel_events:
+            kernel_events[0].record()
+        self.k.step(self.prob, flux, cfl, dx, t_end, self.n, self.Q[a], self.lo[a], self.hi[a], self.Q[b], self.lo[b], self.hi[b],
+                    self.scal, self.ghost_mask)
+        if kernel_events:
+            kernel_events[1].record()
+        self._halo_exchange(b)
+        self._allreduce_lambda((self.n + 1) % 3)
+        self.n += 1
+
+    def advance(self, t_end, flux=L.HLL, cfl=0.6, dx=None, max_steps=1 << 30, check_every=32):
+        done = 0
+        while done < max_steps:
+            if not (self.t[0] < t_end):
+                break
+            m = min(check_every, max_steps - done)
+            for _ in range(m):
+                self.step(flux, cfl, dx, t_end)
+            done += m
+        self.check_status()
+        return done
+
+
+class EnsembleSolver(_Base):
+    """`nprob_global` independent problems of `ncells` cells partitioned over the ranks; every
+    problem keeps its own dt / t.  No communication while stepping."""
+
+    def __init__(self, kernels, ncells, nprob_global, group=None):
+        self.k = kernels
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.p0 = nprob_global * self.rank // self.world
+        self.p1 = nprob_global * (self.rank + 1) // self.world
+        self.nprob = self.p1 - self.p0
+        self.ncells, self.nvar = int(ncells), kernels.nvar
+        self.prob = kernels.problem(self.ncells, self.nprob)
+        tot = self.ncells * self.nprob
+        self.Q = [kernels.empty(self.nvar, tot) for _ in range(2)]
+        self.lo = [kernels.empty(tot) for _ in range(2)]
+        self.hi = [kernels.empty(tot) for _ in range(2)]
+        self.scal = kernels.zeros(scal_size(self.nprob))
+        self._views()
+        self.n = 0
+
+    def set_local(self, Q_local):
+        """(nprob_local, ncells, nvar) Julia layout."""
+        aos = torch.as_tensor(np.ascontiguousarray(Q_local, dtype=np.float64)).to(self.k.device).reshape(-1, self.nvar)
+        assert aos.shape[0] == self.ncells * self.nprob
+        self.set_local_device(aos)
+
+    def set_local_device(self, aos):
+        self.scal.zero_()
+        self.n = 0
+        self.k.aos_to_soa(self.prob, aos, self.Q[0])
+        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self.check_status()
+
+    def local(self):
+        aos = self.k.empty(self.ncells * self.nprob, self.nvar)
+        self.k.soa_to_aos(self.prob, self.Q[self.n & 1], aos)
+        return aos.cpu().numpy().reshape(self.nprob, self.ncells, self.nvar)
+
+    def local_aos_host(self):
+        return self.local().reshape(-1, self.nvar)
+
+    def step_host(self, host_in, host_out, flux=L.HLL, cfl=0.6, dx=None):
+        if not hasattr(self, "_stage"):
+            self._stage = self.k.empty(self.ncells * self.nprob, self.nvar)
+        self._stage.copy_(host_in, non_blocking=True)
+        self.scal.zero_()
+        self.n = 0
+        self.k.aos_to_soa(self.prob, self._stage, self.Q[0])
+        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self.step(flux, cfl, dx)
+        self.k.soa_to_aos(self.prob, self.Q[self.n & 1], self._stage)
+        host_out.copy_(self._stage, non_blocking=True)
+        torch.cuda.current_stream(self.k.device).synchronize()
+
+    def step(self, flux=L.HLL, cfl=0.6, dx=None, t_end=1.0e300, kernel_events=None):
+        dx = 1.0 / self.ncells if dx is None else dx
+        a, b = self.n & 1, (self.n & 1) ^ 1
+        if kernel_events:
+            kernel_events[0].record()
+        self.k.step(self.prob, flux, cfl, dx, t_end, self.n, self.Q[a], self.lo[a], self.hi[a], self.Q[b], self.lo[b], self.hi[b],
+                    self.scal, 0)
+        if kernel_events:
+            kernel_events[1].record()
+        self.n += 1
+
+    def advance(self, t_end, flux=L.HLL, cfl=0.6, dx=None, max_steps=1 << 30, check_every=32):
+        done = 0
+        while done < max_steps:
+            if not (self.t < t_end).any():
+                break
+            m = min(check_every, max_steps - done)
+            for _ in range(m):
+                self.step(flux, cfl, dx, t_end)
+            done += m
+        self.check_status()
+        return done

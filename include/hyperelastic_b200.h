@@ -140,10 +140,17 @@ int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa_dev, double* aos_de
 /* CFL sweep: fills lo, hi and lambda_max slot `slot` of scal (after zeroing it) */
 int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* lo, double* hi, double* scal, int slot, void* stream);
 /* one fused step n: reads Qin/lo_in/hi_in and slot n%3, writes Qout/lo_out/hi_out and slot (n+1)%3;
- * if dt_hist != NULL the step's dt of problem p is stored at dt_hist[p*hist_cap + hist_k] */
+ * if dt_hist != NULL the step's dt of problem p is stored at dt_hist[p*hist_cap + hist_k].
+ * ghost_mask bit 0 / bit 1: the first / last cell of the array is a halo copy of a neighbouring
+ * slab's cell (not written, not counted in lambda_max) instead of a frozen physical boundary cell
+ * (main.jl:219-220). */
 int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n,
              const double* Qin, const double* lo_in, const double* hi_in, double* Qout, double* lo_out, double* hi_out,
-             double* scal, double* dt_hist, int64_t hist_k, int64_t hist_cap, void* stream);
+             double* scal, double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, void* stream);
+/* halo of a slab (nprob == 1): unpack == 0 packs [Q(nvar), lo, hi] of the first / last OWNED cell
+ * (index 1 / ncells-2) into left / right (nvar+2 doubles each); unpack == 1 stores left / right into
+ * the halo cells (index 0 / ncells-1).  mask bit 0 / 1: a left / right neighbour exists. */
+int hsd_halo(const hsd_problem_t* p, double* Q, double* lo, double* hi, double* left, double* right, int mask, int unpack, void* stream);
 /* address (device pointer) of the lambda_max slot that step n WRITES, as doubles [nprob]:
  * the buffer to all-reduce(max) across ranks between step n and n+1 */
 double* hsd_scal_lambda_next(double* scal, int64_t nprob, int64_t n);

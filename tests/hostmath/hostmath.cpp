@@ -20,4 +20,6 @@ void hm_phase(const double* eos_abi, int gen, double alpha, const double* m, dou
   out[k++] = s.bad;
 }
 void hm_sym3_eigs(const double* a, double* ev) { sym3_eigs(a, ev); }
+void hm_sym3_eigs_jacobi(const double* a, double* ev) { sym3_eigs_jacobi(a, ev); }
+double hm_sym3_max_abs(const double* a) { return sym3_max_abs_eig(a); }
 }

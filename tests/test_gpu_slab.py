@@ -1,0 +1,119 @@
+"""GPU: the torch-plumbed device-pointer path (hyperelasticsolver_b200/slab.py) -- the one
+bench.py and the multi-GPU driver use -- against the oracle and against the C-ABI context."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from util import random_mph_prims, relerr
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_slab_solver_single_gpu(gpu, oracle):
+    import torch
+    from hyperelasticsolver_b200.slab import CudaKernels, SlabSolver
+    hs = gpu
+    eos = (hs.Barton2009(), hs.Barton2009())
+    nx, nsteps = 333, 12
+    Ql, Qr = hs.initial_states(eos, 6)
+    Q0 = hs.initial_condition(Ql, Qr, nx)
+    sol = SlabSolver(CudaKernels(eos, hs.MPH30, "cuda:0"), nx)
+    sol.set_from_global(Q0)
+    for _ in range(nsteps):
+        sol.step(hs.HLL, 0.6, 1.0 / nx)
+    Q = sol.gather()
+    ref = oracle.run(None, oracle.MPH30, oracle.HLL, Q0, 0.6, 1.0 / nx, 1e9, nsteps, nthreads=8)
+    assert relerr(Q, ref["Q"]) < 1e-9
+    assert abs(sol.t[0] - ref["t"][0]) < 1e-11 * ref["t"][0] and sol.steps[0] == nsteps
+    # same bits as the C-ABI context path
+    with hs.Solver(eos, nx) as s2:
+        s2.upload(Q0); s2.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=nsteps)
+        assert np.array_equal(s2.download(), Q)
+    # host-slab step (pinned buffers)
+    hin = torch.as_tensor(Q0).pin_memory(); hout = torch.empty_like(hin).pin_memory()
+    sol.step_host(hin, hout, hs.HLL, 0.6, 1.0 / nx)
+    one = oracle.run(None, oracle.MPH30, oracle.HLL, Q0, 0.6, 1.0 / nx, 1e9, 1, nthreads=8)
+    assert relerr(hout.numpy(), one["Q"]) < 1e-12
+
+
+def test_step_host_c_abi(gpu, oracle):
+    hs = gpu
+    eos = hs.Barton2009()
+    nx = 257
+    Ql, Qr = hs.hyperelasticity.initial_states(eos, 2)
+    Q0 = hs.initial_condition(Ql, Qr, nx)
+    with hs.Solver(eos, nx, model=hs.SP13) as sol:
+        Q1, dt = sol.step_host(Q0, None, "hll", 0.6, 1.0 / nx)
+    one = oracle.run([oracle.barton2009()], oracle.SP13, oracle.HLL, Q0, 0.6, 1.0 / nx, 1e9, 1)
+    assert abs(dt[0] - one["dt"][0, 0]) < 1e-13 * dt[0]
+    assert relerr(Q1, one["Q"]) < 1e-12
+
+
+def test_ensemble_solver(gpu, oracle):
+    from hyperelasticsolver_b200.slab import CudaKernels, EnsembleSolver
+    hs = gpu
+    rng = np.random.default_rng(9)
+    eos = (hs.Barton2009(), hs.Barton2009())
+    nprob, nx, nsteps = 5, 130, 10       # 130 cells: two tiles per problem with a nearly empty last tile
+    Ql = hs.prim2cons_mph(eos, random_mph_prims(rng, nprob, spread=0.03)); Qr = hs.prim2cons_mph(eos, random_mph_prims(rng, nprob, spread=0.03))
+    Q0 = np.stack([hs.initial_condition(Ql[i], Qr[i], nx) for i in range(nprob)])
+    sol = EnsembleSolver(CudaKernels(eos, hs.MPH30, "cuda:0"), nx, nprob)
+    sol.set_local(Q0)
+    for _ in range(nsteps):
+        sol.step(hs.HLL, 0.6, 1.0 / nx)
+    ref = oracle.run(None, oracle.MPH30, oracle.HLL, Q0, 0.6, 1.0 / nx, 1e9, nsteps, nthreads=8)
+    assert relerr(sol.local().reshape(-1, 30), ref["Q"].reshape(-1, 30)) < 1e-9
+    assert np.allclose(sol.t, ref["t"], rtol=1e-11)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _nccl_worker(rank, world, port, nx, nsteps, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import hyperelasticsolver_b200 as hs
+        from hyperelasticsolver_b200.slab import CudaKernels, SlabSolver
+        eos = hs.Barton2009()
+        Ql, Qr = hs.hyperelasticity.initial_states(eos, 1, device=rank)
+        Q0 = hs.initial_condition(Ql, Qr, nx)
+        sol = SlabSolver(CudaKernels(eos, hs.SP13, f"cuda:{rank}"), nx)
+        sol.set_from_global(Q0)
+        for _ in range(nsteps):
+            sol.step(hs.HLL, 0.6, 1.0 / nx)
+        Q = sol.gather()
+        if rank == 0:
+            with hs.Solver(eos, nx, model=hs.SP13, device=0) as s1:
+                s1.upload(Q0); s1.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=nsteps)
+                q.put((np.array_equal(s1.download(), Q), float(s1.t[0]), float(sol.t[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_slab_bit_identical(gpu):
+    """2^n-independent check of BASELINE config 3's requirement: the slab-decomposed run is
+    bit-identical to the single-GPU run (only an exact max crosses ranks)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, 5000, 25, q)) for r in range(2)]
+    for p in procs: p.start()
+    same, t1, t2 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120); assert p.exitcode == 0
+    assert same and t1 == t2

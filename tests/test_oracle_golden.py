@@ -26,9 +26,9 @@ def _states(oracle, tc):
 
 def test_quadrature(oracle, B):
     x, w = oracle.quadrature(False)
-    assert np.allclose(x, B["gl6_nodes"], rtol=0, atol=1e-16) and np.allclose(w, B["gl6_weights"], rtol=0, atol=1e-16)
+    assert np.allclose(x, B["gl6_nodes"], rtol=0, atol=3e-16) and np.allclose(w, B["gl6_weights"], rtol=0, atol=3e-16)
     x, w = oracle.quadrature(True)
-    assert np.allclose(x, B["lobatto6_nodes"], rtol=0, atol=2e-16) and np.allclose(w, B["lobatto6_weights"], rtol=0, atol=1e-16)
+    assert np.allclose(x, B["lobatto6_nodes"], rtol=0, atol=5e-16) and np.allclose(w, B["lobatto6_weights"], rtol=0, atol=5e-16)  # survey values carry the ulp noise of a computed rule
     assert abs(w.sum() - 1) < 1e-15
 
 
@@ -131,18 +131,28 @@ def test_conservation_tc6(oracle):
         assert abs((tot1 - tot0) - budget) < 1e-10 * max(1.0, abs(tot0))
 
 
+def sp_to_mph(Qsp):
+    """two identical phases at alpha = 1/2 carrying Q_SP/2 each (F row-major -> column-major)."""
+    Qsp = np.asarray(Qsp)
+    n = Qsp.shape[0]
+    ph = np.zeros((n, 15))
+    ph[:, 0] = 0.5
+    ph[:, 2:5] = 0.5 * Qsp[:, 0:3]
+    ph[:, 5] = 0.5 * Qsp[:, 12]
+    ph[:, 6:15] = 0.5 * Qsp[:, 3:12].reshape(n, 3, 3).transpose(0, 2, 1).reshape(n, 9)
+    return np.concatenate([ph, ph], axis=1)
+
+
 def test_sp_matches_mph_identical_phases(oracle):
-    """MPh with two identical phases at alpha = 1/2 reduces to the one-phase model:
-    Q_mph[phase] = Q_SP / 2 (F column- vs row-major)."""
+    """the shipped two-phase algorithm with two identical phases at alpha = 1/2
+    reduces to the one-phase model: Q_mph[phase] = Q_SP / 2 (F column- vs row-major)."""
     Pl, Pr = sp_primitive_states(1)
     Qs, _ = oracle.prim2cons(None, oracle.SP13, np.stack([Pl, Pr]))
     nx, n = 60, 20
-    rs = oracle.run(None, oracle.SP13, oracle.HLL, riemann_grid(Qs[0], Qs[1], nx), 0.6, 1 / nx, 1e9, n)
-    Ql, Qr = _states(oracle, 4)
-    rm = oracle.run(None, oracle.MPH30, oracle.HLL, riemann_grid(Ql, Qr, nx), 0.6, 1 / nx, 1e9, n)
+    Q0 = riemann_grid(Qs[0], Qs[1], nx)
+    rs = oracle.run(None, oracle.SP13, oracle.HLL, Q0, 0.6, 1 / nx, 1e9, n)
+    rm = oracle.run(None, oracle.MPH30, oracle.HLL, sp_to_mph(Q0), 0.6, 1 / nx, 1e9, n)
     assert np.allclose(rs["dt"][0], rm["dt"][0], rtol=1e-13)
-    Qm, Qsp = rm["Q"], rs["Q"]
-    assert np.allclose(2 * Qm[:, 2:5], Qsp[:, 0:3], rtol=0, atol=1e-12)
-    assert np.allclose(2 * Qm[:, 5], Qsp[:, 12], rtol=1e-12)
-    Fm = 2 * Qm[:, 6:15].reshape(nx, 3, 3).transpose(0, 2, 1).reshape(nx, 9)   # column-major -> row-major
-    assert np.allclose(Fm, Qsp[:, 3:12], rtol=0, atol=1e-12)
+    got = rm["Q"].copy(); want = sp_to_mph(rs["Q"])
+    got[:, [1, 16]] = 0.0     # alpha*rho is passive and absent from the 13-variable model
+    assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
