@@ -47,7 +47,13 @@ long long* scal_steps(double* s, int64_t nprob) { return reinterpret_cast<long l
 int* scal_status(double* s, int64_t nprob) { return reinterpret_cast<int*>(s + HS_SCAL_SLOTS * nprob); }
 
 // threads per block of the fused step / sweep kernels
-constexpr int T_STEP_MPH = 128, T_STEP_SP = 128, T_FACE = 64;
+#ifndef HS_T_STEP_MPH
+#define HS_T_STEP_MPH 128
+#endif
+#ifndef HS_T_STEP_SP
+#define HS_T_STEP_SP 128
+#endif
+constexpr int T_STEP_MPH = HS_T_STEP_MPH, T_STEP_SP = HS_T_STEP_SP, T_FACE = 64;
 
 template <int MODEL, int FLUX, bool GEN, int T>
 int launch_step_t(const StepArgs& a, int64_t nblocks, cudaStream_t st) {

@@ -84,6 +84,30 @@ __device__ __forceinline__ void noncons_column(const PhaseState& st, const doubl
   }
 }
 
+// acc += w * (column 1 of the non-conservative block): same arithmetic as noncons_column with
+// the quadrature weight folded into the common factors (saves the separate multiply-accumulate).
+__device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const double* A, double w, double* acc) {
+  const double To = __shfl_xor_sync(FULL, st.T, 1);
+  double uo[3], so[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { uo[k] = __shfl_xor_sync(FULL, st.u[k], 1); so[k] = __shfl_xor_sync(FULL, st.sig1[k], 1); }
+  const double uI[3] = {0.5 * st.u[0] + 0.5 * uo[0], 0.5 * st.u[1] + 0.5 * uo[1], 0.5 * st.u[2] + 0.5 * uo[2]};
+  const double wi = w / (st.T + To);
+  const double n0 = To * st.sig1[0] + st.T * so[0], n1 = To * st.sig1[1] + st.T * so[1], n2 = To * st.sig1[2] + st.T * so[2];
+  acc[0] += w * uI[0];
+  acc[2] += wi * n0; acc[3] += wi * n1; acc[4] += wi * n2;
+  acc[5] += wi * (n0 * uI[0] + n1 * uI[1] + n2 * uI[2]);
+  const double dv[3] = {uI[0] - st.u[0], uI[1] - st.u[1], uI[2] - st.u[2]};
+  const double wia = w * st.inv_alpha;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double t = wia * A[3 * j];
+    acc[6 + 3 * j] += t * st.u[0] + wia * (A[3 * j] * dv[0] + A[3 * j + 1] * dv[1] + A[3 * j + 2] * dv[2]);
+    acc[7 + 3 * j] += t * st.u[1];
+    acc[8 + 3 * j] += t * st.u[2];
+  }
+}
+
 // acc[j] += dalpha * sum_q w_q c_j(psi(s_q)),  psi(s) = a (1-s) + b s        (NumFluxes.jl:97-107)
 // a, b: shared-memory columns (row stride T) of this thread's phase.  MPh only.
 template <bool GEN, int T>
@@ -103,11 +127,7 @@ __device__ __forceinline__ void path_integral(const EosDev& eos, const double* a
     PhaseState st;
     phase_state<GEN>(eos, alpha, m, E, A, st);
     bad |= st.bad;
-    double c[15];
-    noncons_column(st, A, c);
-#pragma unroll
-    for (int j = 0; j < 15; ++j)
-      if (j != 1) acc[j] += w * c[j];
+    noncons_accumulate(st, A, w, acc);
   }
 }
 
@@ -205,8 +225,11 @@ struct StepArgs {
 
 template <int T> constexpr size_t step_smem_bytes() { return sizeof(double) * (45 * T + 2 * T + 32); }
 
+#ifndef HS_STEP_MINBLOCKS
+#define HS_STEP_MINBLOCKS 4
+#endif
 template <int MODEL, int FLUX, bool GEN, int T>
-__global__ void __launch_bounds__(T) k_step(const StepArgs g) {
+__global__ void __launch_bounds__(T, HS_STEP_MINBLOCKS) k_step(const StepArgs g) {
   using MT = ModelTraits<MODEL>;
   constexpr int NPH = MT::NPH, CPB = T / NPH, J0 = MT::J0;
   extern __shared__ double smem[];

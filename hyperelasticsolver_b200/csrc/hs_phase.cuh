@@ -26,8 +26,10 @@
 
 #ifdef __CUDACC__
 #define HS_HD __host__ __device__ __forceinline__
+#define HS_HD_COLD __host__ __device__ __noinline__
 #else
 #define HS_HD inline
+#define HS_HD_COLD inline
 #endif
 
 namespace hs {
@@ -211,10 +213,55 @@ HS_HD void sym3_eigs_jacobi(const double* s6, double* ev) {
   ev[1] = fmax(fmin(a00, a11), fmin(fmax(a00, a11), a22));   // median
   ev[2] = fmax(a00, fmax(a11, a22));
 }
-HS_HD double sym3_max_abs_eig(const double* a) {
+// rare path of sym3_max_abs_eig: full Jacobi solve (accurate for any degeneracy), kept out of line
+HS_HD_COLD double sym3_max_abs_eig_cold(const double* a) {
   double ev[3];
-  sym3_eigs(a, ev);
-  return fmax(fabs(ev[2]), fabs(ev[0]));
+  sym3_eigs_jacobi(a, ev);
+  return fmax(fabs(ev[0]), fabs(ev[2]));
+}
+
+// approximate reciprocal (about 20 good bits); only used inside self-correcting Newton iterations
+HS_HD double hs_rcp_approx(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+#else
+  return (double)(1.0f / (float)x);
+#endif
+}
+
+// Largest |eigenvalue| of a symmetric 3x3 [11,12,13,22,23,33] -- the hot-path eigen-solve.
+// With q = tr/3, p^2 = |A - qI|_F^2 / 6, r = det(A - qI) / (2 p^3) the eigenvalues are q + p mu_k,
+// mu^3 - 3 mu - 2 r = 0, mu_k = 2 cos((acos r + 2 pi k)/3).  The largest root mu in [1, 2] is found
+// by Newton from above (monotone: f is convex and increasing right of it), started from a cubic
+// over-estimate of 2cos(acos(r)/3); the division uses an approximate reciprocal because the
+// iteration is self-correcting.  lambda_max >= |lambda_min| is guaranteed when p <= 2q (lambda_min
+// >= q - 2p, lambda_max >= q + p), which always holds for a positive-definite acoustic tensor; any
+// other case, and the neighbourhood of a degenerate largest pair (r -> -1, where every
+// characteristic-polynomial method loses sqrt(eps)), takes the out-of-line Jacobi solve.
+HS_HD double sym3_max_abs_eig(const double* a) {
+  const double q = (a[0] + a[3] + a[5]) * (1.0 / 3.0);
+  const double p1 = a[1] * a[1] + a[2] * a[2] + a[4] * a[4];
+  const double b0 = a[0] - q, b3 = a[3] - q, b5 = a[5] - q;
+  const double p2 = (b0 * b0 + b3 * b3 + b5 * b5 + 2.0 * p1) * (1.0 / 6.0);
+  if (!(p2 > 0.0)) return fabs(q);
+  const double ip = hs_rsqrt(p2);
+  const double p = p2 * ip;
+  const double detb = b0 * (b3 * b5 - a[4] * a[4]) - a[1] * (a[1] * b5 - a[4] * a[2]) + a[2] * (a[1] * a[4] - b3 * a[2]);
+  double r = 0.5 * detb * (ip * ip * ip);
+  r = fmin(1.0, fmax(-1.0, r));
+  if (r >= -0.875 && p <= 2.0 * q) {
+    double mu = 1.7464452327513027 + r * (0.32800957660022223 + r * (-0.1425897443947186 + r * 0.08116787571408166));
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const double m2 = mu * mu;
+      const double f = mu * (m2 - 3.0) - 2.0 * r;
+      mu = mu - f * hs_rcp_approx(3.0 * m2 - 3.0);
+    }
+    return q + p * mu;
+  }
+  return sym3_max_abs_eig_cold(a);
 }
 
 // Symmetrised acoustic tensor for n = (1,0,0):
