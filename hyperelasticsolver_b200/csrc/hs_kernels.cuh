@@ -85,14 +85,15 @@ __device__ __forceinline__ void noncons_column(const PhaseState& st, const doubl
 }
 
 // acc += w * (column 1 of the non-conservative block): same arithmetic as noncons_column with
-// the quadrature weight folded into the common factors (saves the separate multiply-accumulate).
+// the quadrature weight folded into the common factors.  (Multiply by the reciprocal: a true FP64
+// division here costs ~10 % of the whole two-phase step.)
 __device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const double* A, double w, double* acc) {
   const double To = __shfl_xor_sync(FULL, st.T, 1);
   double uo[3], so[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) { uo[k] = __shfl_xor_sync(FULL, st.u[k], 1); so[k] = __shfl_xor_sync(FULL, st.sig1[k], 1); }
   const double uI[3] = {0.5 * st.u[0] + 0.5 * uo[0], 0.5 * st.u[1] + 0.5 * uo[1], 0.5 * st.u[2] + 0.5 * uo[2]};
-  const double wi = w / (st.T + To);
+  const double wi = w * (1.0 / (st.T + To));
   const double n0 = To * st.sig1[0] + st.T * so[0], n1 = To * st.sig1[1] + st.T * so[1], n2 = To * st.sig1[2] + st.T * so[2];
   acc[0] += w * uI[0];
   acc[2] += wi * n0; acc[3] += wi * n1; acc[4] += wi * n2;

@@ -270,41 +270,32 @@ HS_HD double sym3_max_abs_eig(const double* a) {
 // dI1 = -2 G_1j, dI2 = I1 dI1 + 2 (G^2)_1j, dI3/I3 = -2 d_1j  (SURVEY.md A.5); only G, G^2 and
 // the scalar energy derivatives enter -- F itself drops out.
 HS_HD void phase_acoustic_sym(const EosDev& eos, const PhaseState& s, double* S6) {
+  // Collecting the terms of -2 (dM^(j)_1i - d_1j M_1i) by tensor structure and symmetrising
+  // (g1, h1 = first rows of G, G^2; b0^2 rB = -2 e2, e1 = -(2/3) e2 I1):
+  //   Omega = -2 { (e2 G11 - a) G + e2 G^2 + (e2/3) g1 g1^T + kg (g1 e_1^T + e_1 g1^T)
+  //                + kh (h1 e_1^T + e_1 h1^T) - (2 dE3c + E3) e_1 e_1^T }
+  //   kg = -a (1 + beta/2) + (beta/4) e1,   kh = e2 (1 + beta),
+  //   dE3c = (k0/2alpha)(alpha/2)(2 rA - 1) rA + (gamma/2)^2 th + (b0^2/2)(beta/2)^2 rB J.
   const double* G = s.G;
-  double G2[6];
-  G2[0] = s.G2r1[0]; G2[1] = s.G2r1[1]; G2[2] = s.G2r1[2];
-  G2[3] = G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
-  G2[4] = G[1] * G[2] + G[3] * G[4] + G[4] * G[5];
-  G2[5] = G[2] * G[2] + G[4] * G[4] + G[5] * G[5];
-  const int ix[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-  const double M1[3] = {s.a * G[0] - s.e2 * G2[0] + s.E3, s.a * G[1] - s.e2 * G2[1], s.a * G[2] - s.e2 * G2[2]};
-  const double b3 = eos.b0sq * s.rB * (1.0 / 3.0);  // d e1 / d I1
-  const double e1 = b3 * s.I1;
+  const double h11 = s.G2r1[0], h12 = s.G2r1[1], h13 = s.G2r1[2];
+  const double h22 = G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
+  const double h23 = G[1] * G[2] + G[3] * G[4] + G[4] * G[5];
+  const double h33 = G[2] * G[2] + G[4] * G[4] + G[5] * G[5];
+  const double e1 = s.a - s.e2 * s.I1;
+  const double cG = -2.0 * (s.e2 * G[0] - s.a);
+  const double cH = -2.0 * s.e2;
+  const double cg = cH * (1.0 / 3.0);
+  const double kg = -2.0 * (0.5 * eos.hbeta * e1 - s.a * (1.0 + eos.hbeta));
+  const double kh = cH * (1.0 + eos.eb);
   const double dE3c = eos.kA1 * eos.ha * s.uc2 + eos.hg * eos.hg * s.th + eos.hb * eos.hbeta * eos.hbeta * s.rB * s.J;
-  double Om[3][3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const double d1j = (j == 0) ? 1.0 : 0.0;
-    const double d3 = -2.0 * d1j;  // dI3 / I3
-    const double dI1 = -2.0 * G[ix[0][j]];
-    const double dI2 = s.I1 * dI1 + 2.0 * G2[ix[0][j]];
-    const double dJ = (2.0 / 3.0) * s.I1 * dI1 - dI2;
-    const double de1 = b3 * dI1 + e1 * eos.hbeta * d3;
-    const double de2 = s.e2 * eos.hbeta * d3;
-    const double da = de1 + de2 * s.I1 + s.e2 * dI1;
-    const double dE3 = dE3c * d3 + eos.hb * eos.hbeta * s.rB * dJ;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double di1 = (i == 0) ? 1.0 : 0.0;
-      const double Gij = G[ix[i][j]];
-      const double dM = da * G[ix[0][i]] - s.a * (G[ix[0][j]] * di1 + Gij) - de2 * G2[ix[0][i]] +
-                        s.e2 * ((G[ix[0][j]] * G[ix[0][i]] + G2[ix[i][j]]) + (G2[ix[0][j]] * di1 + G[0] * Gij)) +
-                        dE3 * di1;
-      Om[i][j] = -2.0 * (dM - d1j * M1[i]);
-    }
-  }
-  S6[0] = Om[0][0]; S6[1] = 0.5 * (Om[0][1] + Om[1][0]); S6[2] = 0.5 * (Om[0][2] + Om[2][0]);
-  S6[3] = Om[1][1]; S6[4] = 0.5 * (Om[1][2] + Om[2][1]); S6[5] = Om[2][2];
+  const double k11 = 2.0 * (2.0 * dE3c + s.E3);
+  const double g1 = G[0], g2 = G[1], g3 = G[2];
+  S6[0] = cG * G[0] + cH * h11 + cg * g1 * g1 + 2.0 * (kg * g1 + kh * h11) + k11;
+  S6[1] = cG * G[1] + cH * h12 + cg * g1 * g2 + (kg * g2 + kh * h12);
+  S6[2] = cG * G[2] + cH * h13 + cg * g1 * g3 + (kg * g3 + kh * h13);
+  S6[3] = cG * G[3] + cH * h22 + cg * g2 * g2;
+  S6[4] = cG * G[4] + cH * h23 + cg * g2 * g3;
+  S6[5] = cG * G[5] + cH * h33 + cg * g3 * g3;
 }
 
 // c_max = sqrt(max_k |eig_k(Omega)|): the only thing any consumer of get_eigvals keeps
