@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -91,17 +91,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def riemann_states(H, model):
+def riemann_states(H, model, device=0):
     if model == "mph30":
         eos = (H.Barton2009(), H.Barton2009())
-        Ql, Qr = H.initial_states(eos, 6)
+        Ql, Qr = H.initial_states(eos, 6, device=device)
         return eos, H.MPH30, Ql, Qr
     eos = H.Barton2009()
-    Ql, Qr = H.hyperelasticity.initial_states(eos, 1)
+    Ql, Qr = H.hyperelasticity.initial_states(eos, 1, device=device)
     return eos, H.SP13, Ql, Qr
 
 
-def ensemble_states(H, model, p0, p1, seed=20261017):
+def ensemble_states(H, model, p0, p1, seed=20261017, device=0):
     """BASELINE config 4 generator: PCG64(20261017), per problem and side
     alpha1~U[0.1,0.9], u~U[-1,1]^3, S~U[0,1e-3], F = I + 0.05 U[-1,1]^(3x3), nominal density 8.9."""
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -117,11 +117,11 @@ def ensemble_states(H, model, p0, p1, seed=20261017):
             P[..., o] = al; P[..., o + 1] = 8.9 / det; P[..., o + 2:o + 5] = u; P[..., o + 5] = S
             P[..., o + 6:o + 15] = F.transpose(0, 1, 3, 2).reshape(p1 - p0, 2, 9)   # column-major
         eos = (H.Barton2009(), H.Barton2009())
-        Q = H.prim2cons_mph(eos, P.reshape(-1, 30)).reshape(p1 - p0, 2, 30)
+        Q = H.prim2cons_mph(eos, P.reshape(-1, 30), device=device).reshape(p1 - p0, 2, 30)
         return eos, H.MPH30, Q
     P = np.concatenate([u, F.reshape(p1 - p0, 2, 9), S[..., None]], axis=-1)
     eos = H.Barton2009()
-    Q = H.hyperelasticity.prim2cons(eos, P.reshape(-1, 13)).reshape(p1 - p0, 2, 13)
+    Q = H.hyperelasticity.prim2cons(eos, P.reshape(-1, 13), device=device).reshape(p1 - p0, 2, 13)
     return eos, H.SP13, Q
 
 
@@ -210,35 +210,38 @@ def run_ours(args):
     flux = L.HLL
     ensemble = "nprob" in wl
 
-    # ---- build the synthetic state on the device (not timed) ------------------------------------
+    # ---- build the synthetic state on the device, directly in SoA (not timed) --------------------
+    def fill_riemann_soa(sol_, ql, qr, left_mask_cells, nprob_local=None):
+        """Q[0][v] = left ? ql[v] : qr[v]; ql/qr: (nvar,) or (nprob_local, nvar) device tensors."""
+        Q0 = sol_.Q[0]
+        for v in range(nvar):
+            if nprob_local is None:
+                Q0[v] = torch.where(left_mask_cells, ql[v], qr[v])
+            else:
+                Q0[v].view(nprob_local, -1)[:] = torch.where(left_mask_cells[None, :], ql[:, v, None], qr[:, v, None])
+        sol_.init_from_soa()
+
     if ensemble:
         nprob_g, ncells = wl["nprob"], wl["cells"]
         p0, p1 = nprob_g * rank // world, nprob_g * (rank + 1) // world
-        eos, hmodel, Qlr = ensemble_states(H, model, p0, p1)
+        eos, hmodel, Qlr = ensemble_states(H, model, p0, p1, device=local)
         kern = CudaKernels(eos, hmodel, dev)
         sol = EnsembleSolver(kern, ncells, nprob_g)
         left = torch.arange(ncells, device=dev) < ncells / 2
         Qlr_d = torch.as_tensor(Qlr, device=dev)
-        chunk = 2048
-        aos = torch.empty(sol.nprob * ncells, nvar, dtype=torch.float64, device=dev)
-        for c0 in range(0, sol.nprob, chunk):
-            q = Qlr_d[c0:c0 + chunk]
-            aos[c0 * ncells:(c0 + q.shape[0]) * ncells] = torch.where(left[None, :, None], q[:, None, 0, :], q[:, None, 1, :]).reshape(-1, nvar)
-        sol.set_local_device(aos)
-        del aos
+        fill_riemann_soa(sol, Qlr_d[:, 0, :].contiguous(), Qlr_d[:, 1, :].contiguous(), left, sol.nprob)
         n_units = nprob_g * ncells
         local_cells = sol.nprob * ncells
         dx = 1.0 / ncells
         updated_local = sol.nprob * (ncells - 2)
     else:
-        eos, hmodel, Ql, Qr = riemann_states(H, model)
+        eos, hmodel, Ql, Qr = riemann_states(H, model, device=local)
         n_global = wl["cells"] * (world if wl["scaling"] == "weak" else 1)
         kern = CudaKernels(eos, hmodel, dev)
         sol = SlabSolver(kern, n_global)
         gidx = torch.arange(sol.lo_g, sol.hi_g, device=dev)
-        aos = torch.where((gidx < n_global / 2)[:, None], torch.as_tensor(Ql, device=dev)[None, :], torch.as_tensor(Qr, device=dev)[None, :]).contiguous()
-        sol.set_local_device(aos)
-        del aos, gidx
+        fill_riemann_soa(sol, torch.as_tensor(Ql, device=dev), torch.as_tensor(Qr, device=dev), gidx < n_global / 2)
+        del gidx
         n_units = n_global
         local_cells = sol.nloc
         dx = 1.0 / n_global
@@ -298,47 +301,59 @@ def run_ours(args):
                 "note": "the path is FP64-pipe bound, not HBM bound (DESIGN.md): see profiles/ for the measured DFMA peak and pipe utilisation"}
 
     # ---- end to end through the host-buffer API ------------------------------------------------
+    # every step: H2D of the whole (pinned) host state, CFL sweep, fused step, D2H of the new state.
+    # Grid: the workload itself when it is <= 2^24 cells per GPU, else a 2^24-cell-per-GPU sample of it
+    # (pinned host buffers of the 2^28 / ensemble workloads would not fit host memory twice).
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    nbytes_state = local_cells * nvar * 8
-    if not ensemble and world == 1:
-        # the reference-facing C-ABI call: hs_step_host on (pinned) host arrays
-        del sol
-        torch.cuda.empty_cache()
-        host_in = torch.empty(local_cells, nvar, dtype=torch.float64, pin_memory=True)
-        host_out = torch.empty(local_cells, nvar, dtype=torch.float64, pin_memory=True)
-        idx = torch.arange(local_cells)
-        host_in.copy_(torch.where((idx < local_cells / 2)[:, None], torch.as_tensor(Ql)[None, :], torch.as_tensor(Qr)[None, :]))
-        hin, hout = host_in.numpy(), host_out.numpy()
-        with H.Solver(eos, local_cells, model=hmodel, device=local) as s2:
-            s2.step_host(hin, hout, "hll", 0.6, dx)     # warm-up (allocations, first-touch)
-            l0 = kern.launches()
-            t0 = time.perf_counter()
-            for i in range(e2e_steps):
-                s2.step_host(hin if i % 2 == 0 else hout, hout if i % 2 == 0 else hin, "hll", 0.6, dx)
-            e2e_t = time.perf_counter() - t0
-            e2e_launches = kern.launches() - l0
-        e2e_api = "hs_step_host (C ABI): upload Q0 + CFL sweep + fused step + download Q1, every step"
+    del sol
+    torch.cuda.empty_cache()
+    if ensemble:
+        nprob_e = min(wl["nprob"], (1 << 24) // wl["cells"] * world)
+        pe0, pe1 = nprob_e * rank // world, nprob_e * (rank + 1) // world
+        sol = EnsembleSolver(kern, wl["cells"], nprob_e)
+        e_cells_local, e_units = sol.nprob * wl["cells"], nprob_e * wl["cells"]
+        host_in = torch.empty(e_cells_local, nvar, dtype=torch.float64, pin_memory=True)
+        host_out = torch.empty_like(host_in).pin_memory()
+        left_h = (torch.arange(wl["cells"]) < wl["cells"] / 2)[None, :, None]
+        q = torch.as_tensor(Qlr[: pe1 - pe0])
+        host_in.view(sol.nprob, wl["cells"], nvar)[:] = torch.where(left_h, q[:, None, 0, :], q[:, None, 1, :])
+        step_host = lambda a, b: sol.step_host(a, b, flux, 0.6, dx)
+        e2e_api = "EnsembleSolver.step_host: pinned host state -> device, CFL sweep, fused step, device -> host, every step"
     else:
-        host_in = torch.empty(local_cells, nvar, dtype=torch.float64, pin_memory=True)
-        host_out = torch.empty(local_cells, nvar, dtype=torch.float64, pin_memory=True)
-        host_in.copy_(torch.as_tensor(sol.local_aos_host()))
-        sol.step_host(host_in, host_out, flux, 0.6, dx)
-        torch.cuda.synchronize(); barrier()
-        l0 = kern.launches()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            sol.step_host(host_in if i % 2 == 0 else host_out, host_out if i % 2 == 0 else host_in, flux, 0.6, dx)
-        torch.cuda.synchronize()
-        e2e_t = time.perf_counter() - t0
-        barrier()
-        e2e_launches = kern.launches() - l0
-        if world > 1:
-            t = torch.tensor([e2e_t], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_t = float(t.item())
-        e2e_api = "SlabSolver/EnsembleSolver.step_host: pinned host slab -> device, CFL sweep (+allreduce), fused step, device -> host, every step"
-    e2e = {"value": n_units * e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": nbytes_state * world, "d2h_bytes_per_step": nbytes_state * world,
-           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_t / e2e_steps, "api": e2e_api, "gpu_launches": e2e_launches}
+        e_cells = min(wl["cells"] if wl["scaling"] == "weak" else wl["cells"] // world, 1 << 24)
+        e_units = e_cells * world
+        if world == 1:
+            s2 = H.Solver(eos, e_cells, model=hmodel, device=local)
+            e_cells_local = e_cells
+            lo_g = 0
+            step_host = lambda a, b: s2.step_host(a.numpy(), b.numpy(), "hll", 0.6, 1.0 / e_units)
+            e2e_api = "hs_step_host (C ABI): upload Q0 + CFL sweep + fused step + download Q1, every step"
+        else:
+            sol = SlabSolver(kern, e_units)
+            e_cells_local, lo_g = sol.nloc, sol.lo_g
+            step_host = lambda a, b: sol.step_host(a, b, flux, 0.6, 1.0 / e_units)
+            e2e_api = "SlabSolver.step_host: pinned host slab -> device, CFL sweep + allreduce, fused step, halo, device -> host, every step"
+        host_in = torch.empty(e_cells_local, nvar, dtype=torch.float64, pin_memory=True)
+        host_out = torch.empty_like(host_in).pin_memory()
+        gi = torch.arange(lo_g, lo_g + e_cells_local)
+        host_in.copy_(torch.where((gi < e_units / 2)[:, None], torch.as_tensor(Ql)[None, :], torch.as_tensor(Qr)[None, :]))
+    step_host(host_in, host_out)                     # warm-up (allocations, first touch)
+    torch.cuda.synchronize(); barrier()
+    l0 = kern.launches()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_host(host_in if i % 2 == 0 else host_out, host_out if i % 2 == 0 else host_in)
+    torch.cuda.synchronize()
+    e2e_t = time.perf_counter() - t0
+    barrier()
+    e2e_launches = kern.launches() - l0
+    if world > 1:
+        t = torch.tensor([e2e_t], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    nbytes_e2e = e_units * nvar * 8
+    e2e = {"value": e_units * e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": nbytes_e2e, "d2h_bytes_per_step": nbytes_e2e,
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_t / e2e_steps, "cells_total": e_units, "api": e2e_api, "gpu_launches_per_rank": e2e_launches}
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
@@ -357,7 +372,7 @@ def run_ours(args):
             "config": {"workload": args.workload, "description": wl["desc"], "model": None, "flux": "hll", "cfl": 0.6,
                        "cells_total": n_units, "cells_per_gpu": local_cells,
                        "parallelism": ("ensemble partition, no collective" if ensemble else f"slab x{world}, halo send/recv + allreduce(max) per step"),
-                       "l2": f"state {nbytes_state / 1e9:.2f} GB per GPU per buffer >> 126 MB L2 (inputs larger than L2, no flush needed)"},
+                       "l2": f"state {local_cells * nvar * 8 / 1e9:.2f} GB per GPU per buffer >> 126 MB L2 (inputs larger than L2, no flush needed)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         out["config"].pop("model")

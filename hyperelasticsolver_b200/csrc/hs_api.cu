@@ -30,6 +30,18 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     }                                                                                              \
   } while (0)
 
+// Switches the calling thread to `dev` and back on scope exit, so the host-buffer entry points never
+// disturb the caller's current device (torch, a Julia CUDA allocator, ...).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static_assert(sizeof(EosDev) <= sizeof(double) * 20, "EosDev must fit hsd_problem_t::eos_dev");
 static_assert(sizeof(hs_barton2009_t) == sizeof(EosAbi), "ABI struct mismatch");
 
@@ -221,11 +233,10 @@ struct hs_ctx {
   int64_t n;          // launch counter since the last upload (selects buffers and scalar slots)
 };
 
-static int ctx_enter(hs_ctx* c) {
-  if (!c) return fail(HS_ERR_ARG, "null context");
-  CU(cudaSetDevice(c->device));
-  return HS_OK;
-}
+#define CTX_ENTER(c)                                             \
+  if (!(c)) return fail(HS_ERR_ARG, "null context");               \
+  DeviceGuard guard_((c)->device);                                 \
+  if (!guard_.ok) return fail(HS_ERR_CUDA, "cudaSetDevice failed")
 
 int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob, int device) {
   if (!out) return fail(HS_ERR_ARG, "null ctx pointer");
@@ -238,7 +249,8 @@ int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase,
   c->device = device;
   c->nvar = model == HS_MODEL_MPH30 ? 30 : 13;
   auto bail = [&](int code) { hs_destroy(c); return code; };
-  if (cudaSetDevice(device) != cudaSuccess) { delete c; return fail(HS_ERR_CUDA, "cudaSetDevice failed"); }
+  DeviceGuard guard_(device);
+  if (!guard_.ok) { delete c; return fail(HS_ERR_CUDA, "cudaSetDevice failed"); }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(HS_ERR_CUDA, "stream creation failed"); }
   const size_t nq = (size_t)c->nvar * c->prob.stride * sizeof(double), nb = (size_t)c->prob.stride * sizeof(double);
   cudaError_t e = cudaSuccess;
@@ -256,7 +268,7 @@ int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase,
 
 int hs_destroy(hs_ctx_t* c) {
   if (!c) return HS_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard guard_(c->device);
   for (int k = 0; k < 2; ++k) { cudaFree(c->Q[k]); cudaFree(c->lo[k]); cudaFree(c->hi[k]); }
   cudaFree(c->scal); cudaFree(c->stage); cudaFree(c->dt_hist);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -278,7 +290,8 @@ static int read_status(hs_ctx* c) {
 }
 
 int hs_upload(hs_ctx_t* c, const double* Q) {
-  int rc = ctx_enter(c); if (rc) return rc;
+  CTX_ENTER(c);
+  int rc = HS_OK;
   if (!Q) return fail(HS_ERR_ARG, "null Q");
   rc = ensure_stage(c); if (rc) return rc;
   const size_t nq = (size_t)c->nvar * c->prob.stride * sizeof(double);
@@ -291,7 +304,8 @@ int hs_upload(hs_ctx_t* c, const double* Q) {
 }
 
 int hs_download(hs_ctx_t* c, double* Q) {
-  int rc = ctx_enter(c); if (rc) return rc;
+  CTX_ENTER(c);
+  int rc = HS_OK;
   if (!Q) return fail(HS_ERR_ARG, "null Q");
   rc = ensure_stage(c); if (rc) return rc;
   rc = hsd_soa_to_aos(&c->prob, c->Q[c->n & 1], c->stage, c->stream); if (rc) return rc;
@@ -301,7 +315,8 @@ int hs_download(hs_ctx_t* c, double* Q) {
 }
 
 int hs_set_time(hs_ctx_t* c, double t, int64_t step) {
-  int rc = ctx_enter(c); if (rc) return rc;
+  CTX_ENTER(c);
+  int rc = HS_OK;
   const int64_t np = c->prob.nprob;
   std::vector<double> tv(np, t);
   std::vector<long long> sv(np, step);
@@ -312,7 +327,8 @@ int hs_set_time(hs_ctx_t* c, double t, int64_t step) {
 }
 
 int hs_wave_speeds(hs_ctx_t* c, double* eig, double* lambda_max) {
-  int rc = ctx_enter(c); if (rc) return rc;
+  CTX_ENTER(c);
+  int rc = HS_OK;
   const int64_t np = c->prob.nprob;
   const int cur = (int)(c->n & 1);
   if (eig) {
@@ -350,7 +366,8 @@ static int ensure_hist(hs_ctx* c, int64_t cap) {
 }
 
 int hs_step(hs_ctx_t* c, int flux, double cfl, double dx, double* dt_out) {
-  int rc = ctx_enter(c); if (rc) return rc;
+  CTX_ENTER(c);
+  int rc = HS_OK;
   rc = ensure_hist(c, 1); if (rc) return rc;
   const int64_t np = c->prob.nprob;
   rc = enqueue_step(c, flux, cfl, dx, 1.0e300, c->dt_hist, 0, 1); if (rc) return rc;
@@ -360,7 +377,8 @@ int hs_step(hs_ctx_t* c, int flux, double cfl, double dx, double* dt_out) {
 
 int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64_t max_steps, double* t_io,
                int64_t* step_io, double* dt_hist) {
-  int rc = ctx_enter(c); if (rc) return rc;
+  CTX_ENTER(c);
+  int rc = HS_OK;
   if (max_steps < 0) return fail(HS_ERR_ARG, "max_steps < 0");
   const int64_t np = c->prob.nprob;
   if (t_io) CU(cudaMemcpyAsync(hsd_scal_time(c->scal, np, c->n), t_io, sizeof(double) * np, cudaMemcpyHostToDevice, c->stream));
@@ -412,16 +430,15 @@ struct DevBuf {
 int stateless_prolog(int model, const hs_barton2009_t* eos, int nphase, int64_t n, int device, hsd_problem_t* p) {
   if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
   if (n < 1) return fail(HS_ERR_ARG, "n < 1");
-  int rc = hsd_problem_init(p, model, eos, nphase, 3, 1);
-  if (rc) return rc;
-  CU(cudaSetDevice(device));
-  return HS_OK;
+  return hsd_problem_init(p, model, eos, nphase, 3, 1);
 }
 
 template <int OP>
 int cellop(int model, const hs_barton2009_t* eos, int nphase, const double* in, double* out, int64_t n, int device) {
   hsd_problem_t p;
   int rc = stateless_prolog(model, eos, nphase, n, device, &p); if (rc) return rc;
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return fail(HS_ERR_CUDA, "cudaSetDevice failed");
   if (!in || !out) return fail(HS_ERR_ARG, "null array");
   const int nvar = model == HS_MODEL_MPH30 ? 30 : 13;
   DevBuf din, dout, dst;
@@ -464,6 +481,8 @@ int faceop(int model, int flux, const hs_barton2009_t* eos, int nphase, const do
            const double* eig_r, double lambda, double* cons, double* dm, double* dp, double* s, int64_t n, int device) {
   hsd_problem_t p;
   int rc = stateless_prolog(model, eos, nphase, n, device, &p); if (rc) return rc;
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return fail(HS_ERR_CUDA, "cudaSetDevice failed");
   if (!Ql || !Qr) return fail(HS_ERR_ARG, "null array");
   if (flux == HS_FLUX_HLL && (!eig_l || !eig_r)) return fail(HS_ERR_ARG, "hll needs the cached eigvals of both cells");
   const int nvar = model == HS_MODEL_MPH30 ? 30 : 13, neig = 6 * nphase;
@@ -528,6 +547,8 @@ int hs_noncons_flux(const hs_barton2009_t* eos, const double* Q, double* col, do
 int hs_get_eigvals(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* eig, int64_t n, int device) {
   hsd_problem_t p;
   int rc = stateless_prolog(model, eos, nphase, n, device, &p); if (rc) return rc;
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return fail(HS_ERR_CUDA, "cudaSetDevice failed");
   if (!Q || !eig) return fail(HS_ERR_ARG, "null array");
   const int nvar = model == HS_MODEL_MPH30 ? 30 : 13, neig = 6 * nphase;
   DevBuf din, dout, dst;

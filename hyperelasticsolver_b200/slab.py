@@ -160,6 +160,14 @@ class SlabSolver(_Base):
         if check:
             self.check_status()
 
+    def init_from_soa(self):
+        """Q[0] was filled in place (structure of arrays): reset the clock and run the CFL sweep."""
+        self.scal.zero_()
+        self.n = 0
+        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self._allreduce_lambda(0)
+        self.check_status()
+
     def local_aos_host(self):
         """(nloc, nvar) host copy of the local slab, halo cells included."""
         aos = self.k.empty(self.nloc, self.nvar)
@@ -277,6 +285,12 @@ class EnsembleSolver(_Base):
         self.scal.zero_()
         self.n = 0
         self.k.aos_to_soa(self.prob, aos, self.Q[0])
+        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self.check_status()
+
+    def init_from_soa(self):
+        self.scal.zero_()
+        self.n = 0
         self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
         self.check_status()
 

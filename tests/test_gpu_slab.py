@@ -117,3 +117,21 @@ def test_two_gpu_slab_bit_identical(gpu):
     for p in procs:
         p.join(timeout=120); assert p.exitcode == 0
     assert same and t1 == t2
+
+
+def test_stateless_calls_keep_current_device(gpu):
+    """The host-buffer entry points must not change the caller's current CUDA device (torch or a
+    Julia allocator may be using another one)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    hs = gpu
+    torch.cuda.set_device(1)
+    x = torch.ones(4, device="cuda")
+    eos = (hs.Barton2009(), hs.Barton2009())
+    Ql, _ = hs.initial_states(eos, 6, device=0)
+    with hs.Solver(eos, 64, device=0) as sol:
+        sol.upload(hs.initial_condition(Ql, Ql, 64)); sol.step()
+    assert torch.cuda.current_device() == 1
+    assert float((x + 1).sum()) == 8.0
+    torch.cuda.set_device(0)
