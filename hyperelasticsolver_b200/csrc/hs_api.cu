@@ -70,7 +70,7 @@ constexpr int T_STEP_MPH = HS_T_STEP_MPH, T_STEP_SP = HS_T_STEP_SP, T_FACE = 64;
 template <int MODEL, int FLUX, bool GEN, int T>
 int launch_step_t(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
   static bool attr_set = false;
-  constexpr size_t smem = step_smem_bytes<T>();
+  constexpr size_t smem = step_smem_bytes<MODEL, T>();
   if (!attr_set) {
     CU(cudaFuncSetAttribute(k_step<MODEL, FLUX, GEN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;

@@ -224,20 +224,30 @@ struct StepArgs {
   EosPair eos;
 };
 
-template <int T> constexpr size_t step_smem_bytes() { return sizeof(double) * (45 * T + 2 * T + 32); }
+// rows J0..14 of the three tile arrays + cached bounds + reduction scratch
+template <int MODEL, int T> constexpr size_t step_smem_bytes() {
+  return sizeof(double) * (3 * (15 - ModelTraits<MODEL>::J0) * T + 2 * T + 32);
+}
 
-#ifndef HS_STEP_MINBLOCKS
-#define HS_STEP_MINBLOCKS 4
+// resident blocks per SM the register allocation is capped for (tuned on B200, profiles/)
+#ifndef HS_MINB_MPH
+#define HS_MINB_MPH 4
+#endif
+#ifndef HS_MINB_SP
+#define HS_MINB_SP 4
 #endif
 template <int MODEL, int FLUX, bool GEN, int T>
-__global__ void __launch_bounds__(T, HS_STEP_MINBLOCKS) k_step(const StepArgs g) {
+__global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MINB_SP)) k_step(const StepArgs g) {
   using MT = ModelTraits<MODEL>;
   constexpr int NPH = MT::NPH, CPB = T / NPH, J0 = MT::J0;
   extern __shared__ double smem[];
-  double* Rs = smem;            // records        [15][T]
-  double* Fs = Rs + 15 * T;     // physical flux  [15][T]
-  double* Hs = Fs + 15 * T;     // Q_hll, then the fluctuation handed to the left cell [15][T]
-  double* lo_s = Hs + 15 * T;   // [CPB]
+  // Three tile arrays of NROW = 15 - J0 rows (the single-phase model has no slots 0,1); the
+  // pointers are biased by -J0 rows so that slot j is always row j.
+  constexpr int NROW = 15 - J0;
+  double* Rs = smem - J0 * T;          // records        [J0..14][T]
+  double* Fs = Rs + NROW * T;          // physical flux  [J0..14][T]
+  double* Hs = Fs + NROW * T;          // Q_hll, then the fluctuation handed to the left cell
+  double* lo_s = smem + 3 * NROW * T;  // [CPB]
   double* hi_s = lo_s + T;      // [CPB]
   double* red = hi_s + T;       // [T/32]
 
@@ -307,13 +317,15 @@ __global__ void __launch_bounds__(T, HS_STEP_MINBLOCKS) k_step(const StepArgs g)
 
   // ---- face between cell l-1 and cell l (hll / lxf, NumFluxes.jl) ---------------------------
   const int tl = (l >= 1) ? tid - NPH : tid;   // halo threads evaluate a dummy face against themselves
-  double CR[15];                               // fluctuation kept by this (right) cell
+  // Two-phase: CR = fluctuation kept by this (right) cell.  Single-phase: the face only has a
+  // conservative flux, so the right cell's share is minus the left cell's (read back from Hs).
+  double CR[MODEL == MODEL_MPH30 ? 15 : 1];
   {
     int fbad = 0;
     double* H = Hs + tid;
     auto emit = [&](int j, double cons, double dm, double dp) {
-      H[j * T] = cons + dm;      // F_r - ... + NF_r of the left cell  (update_cell, main.jl:57-59)
-      CR[j] = dp - cons;         // - F_l + NF_l of this cell
+      H[j * T] = cons + dm;                              // F_r + NF_r of the left cell  (update_cell, main.jl:57-59)
+      if (MODEL == MODEL_MPH30) CR[j] = dp - cons;       // - F_l + NF_l of this cell
     };
     face_eval<MODEL, FLUX, GEN, T>(eos, Rs + tl, Rs + tid, Fs + tl, Fs + tid, lo_s[(l >= 1) ? l - 1 : l], hi_s[l],
                                    lambda, H, fbad, nullptr, emit);
@@ -329,7 +341,8 @@ __global__ void __launch_bounds__(T, HS_STEP_MINBLOCKS) k_step(const StepArgs g)
 #pragma unroll
     for (int j = J0; j < 15; ++j) {
       const double q = Rs[j * T + tid];
-      qn[j] = own_interior ? q - upd * (Hs[j * T + tr] + CR[j]) : q;
+      const double mine = (MODEL == MODEL_MPH30) ? CR[j] : -Hs[j * T + tid];
+      qn[j] = own_interior ? q - upd * (Hs[j * T + tr] + mine) : q;
     }
     if (own_interior) {
       if (MODEL == MODEL_MPH30) {
