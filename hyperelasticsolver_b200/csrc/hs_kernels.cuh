@@ -27,6 +27,16 @@ constexpr unsigned FULL = 0xffffffffu;
 
 struct EosPair { EosDev e[2]; };
 
+// max over the warp of a NON-NEGATIVE double: such doubles order like their bit patterns, so two
+// 32-bit redux.sync (high word, then low word among the lanes that hold the winning high word)
+// replace five shuffle + compare rounds.
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(FULL, hi);
+  const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
 // gausslegendre(6) / gausslobatto(6) mapped to [0,1] as NumFluxes.jl:95 / :37 do.
 __constant__ double c_gleg_x[6] = {(-0.9324695142031520278 + 1.0) / 2.0, (-0.6612093864662645137 + 1.0) / 2.0,
                                    (-0.2386191860831969086 + 1.0) / 2.0, (0.2386191860831969086 + 1.0) / 2.0,
@@ -258,28 +268,36 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
   const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
   const EosDev& eos = g.eos.e[ph];
 
-  const double lam_cur = __longlong_as_double((long long)g.lam[(size_t)g.cur * g.nprob + prob]);
-  const double t_cur = g.tt[(size_t)g.cur * g.nprob + prob];
-  const bool active = t_cur < g.t_end;                   // while t < T, main.jl:202
-  const double dt = g.cfl * g.dx / lam_cur;              // main.jl:212
-  const double dtdx = dt / g.dx;                         // main.jl:225
-  const double lambda = g.dx / dt;                       // main.jl:223
-  const double upd = (FLUX == FLUX_HLL) ? dtdx : 1.0 / lambda;  // main.jl:59 / :40
+  // Issue every global load of the block back to back (two per-problem scalars, the tile, the
+  // cached bounds) before anything consumes them, so their latencies overlap.
+  const unsigned long long lam_bits = __ldg(g.lam + (size_t)g.cur * g.nprob + prob);
+  const double t_cur = __ldg(g.tt + (size_t)g.cur * g.nprob + prob);
+  double rin[15], lo_in_r = 0.0, hi_in_r = 0.0;
+  if (MODEL == MODEL_MPH30) {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) rin[j] = __ldg(g.Qin + (size_t)(15 * ph + j) * g.stride + gi);
+  } else {
+#pragma unroll
+    for (int v = 0; v < 13; ++v) rin[sp_slot(v)] = __ldg(g.Qin + (size_t)v * g.stride + gi);
+  }
+  if (ph == 0) { lo_in_r = __ldg(g.lo_in + gi); hi_in_r = __ldg(g.hi_in + gi); }
 
   const bool own_interior = valid && l >= 1 && l <= CPB - 2 && c <= g.ncells - 2;
   // frozen physical boundary cells, main.jl:219-220 (halo cells of a slab are neither written nor
   // counted in lambda_max: their owner does both)
   const bool own_frozen = valid && ((c == 0 && !(g.ghost & 1)) || (c == g.ncells - 1 && !(g.ghost & 2)));
 
-  // ---- load the tile ----------------------------------------------------------------------
-  if (MODEL == MODEL_MPH30) {
+  // ---- stage the tile in shared memory -------------------------------------------------------
 #pragma unroll
-    for (int j = 0; j < 15; ++j) Rs[j * T + tid] = __ldg(g.Qin + (size_t)(15 * ph + j) * g.stride + gi);
-  } else {
-#pragma unroll
-    for (int v = 0; v < 13; ++v) Rs[sp_slot(v) * T + tid] = __ldg(g.Qin + (size_t)v * g.stride + gi);
-  }
-  if (ph == 0) { lo_s[l] = __ldg(g.lo_in + gi); hi_s[l] = __ldg(g.hi_in + gi); }
+  for (int j = J0; j < 15; ++j) Rs[j * T + tid] = rin[j];
+  if (ph == 0) { lo_s[l] = lo_in_r; hi_s[l] = hi_in_r; }
+
+  const double lam_cur = __longlong_as_double((long long)lam_bits);
+  const bool active = t_cur < g.t_end;                   // while t < T, main.jl:202
+  const double dt = g.cfl * g.dx / lam_cur;              // main.jl:212
+  const double dtdx = dt / g.dx;                         // main.jl:225
+  const double lambda = g.dx / dt;                       // main.jl:223
+  const double upd = (FLUX == FLUX_HLL) ? dtdx : 1.0 / lambda;  // main.jl:59 / :40
 
   if (!active) {  // this problem already reached t_end: carry the state through unchanged
     if (own_interior || own_frozen) {
@@ -380,8 +398,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     }
   }
   // ---- block max of lambda, one atomic per block ---------------------------------------------
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lamv = fmax(lamv, __shfl_xor_sync(FULL, lamv, o));
+  lamv = warp_max_nonneg(lamv);
   if ((tid & 31) == 0) red[tid >> 5] = lamv;
   bad = __any_sync(FULL, bad);
   if (bad && (tid & 31) == 0) atomicOr(g.status, 1);
@@ -453,8 +470,7 @@ __global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, doub
       }
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lamv = fmax(lamv, __shfl_xor_sync(FULL, lamv, o));
+  lamv = warp_max_nonneg(lamv);
   if ((tid & 31) == 0) red[tid >> 5] = lamv;
   bad = __any_sync(FULL, bad);
   if (bad && (tid & 31) == 0) atomicOr(status, 1);

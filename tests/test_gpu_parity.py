@@ -198,3 +198,30 @@ def test_domain_error(gpu):
     bad = Ql.copy(); bad[6:15] *= -1.0       # det(F) < 0 -> sqrt(negative) in cons2prim (HyperelasticityMPh.jl:114)
     with pytest.raises(hs.DomainError):
         hs.cons2prim_mph(eos, bad)
+
+
+def test_driver_default_run_matches_oracle(gpu, oracle, tmp_path):
+    """The shipped default configuration in miniature through the main.jl-compatible driver:
+    CSV snapshots every log_freq steps, result.csv, restart from the last snapshot."""
+    import logging
+    from hyperelasticsolver_b200 import driver
+    hs = gpu
+    eos = (hs.Barton2009(), hs.Barton2009())
+    d = str(tmp_path / "barton_data") + "/"
+    nx, T = 120, 0.012
+    Q, t, steps = driver.run(eos, 6, nx, 0.6, T, 1.0, 10, d, "hll", 0, None, logging.getLogger("test"))
+    Ql, Qr = hs.initial_states(eos, 6)
+    ref = oracle.run(None, oracle.MPH30, oracle.HLL, hs.initial_condition(Ql, Qr, nx), 0.6, 1.0 / nx, T, 10000, nthreads=8)
+    assert steps == ref["steps"][0] and abs(t - ref["t"][0]) < 1e-12 * T
+    assert relerr(Q, ref["Q"]) < 1e-9
+    import os
+    files = sorted(os.listdir(d))
+    assert files[0] == "result.csv" and "sol_000000.csv" in files and f"sol_{(steps // 10) * 10:06d}.csv" in files
+    P, n = driver.read_data(os.path.join(d, "result.csv"))
+    Po, _ = oracle.cons2prim(None, oracle.MPH30, ref["Q"])
+    assert n == nx and relerr(P, Po) < 1e-8
+    # tanh-smoothed initial condition (main.jl:110-123): alpha profile and alpha1 + alpha2 = 1
+    Q0 = driver.initial_condition_tanh(eos, Ql, Qr, nx, 0.2)
+    x = (np.arange(1, nx + 1) - 0.5) / nx
+    assert np.allclose(Q0[:, 0], 0.1 * (np.tanh(4 * (x - 0.5) / 0.2) + 1) + 0.4, rtol=1e-15)
+    assert np.allclose(Q0[:, 0] + Q0[:, 15], 1.0, rtol=0, atol=1e-16)
