@@ -18,6 +18,7 @@ SP13, MPH30 = 0, 1
 LXF, HLL = 0, 1
 NVAR = {SP13: 13, MPH30: 30}
 NPHASE = {SP13: 1, MPH30: 2}
+NAUX = {SP13: 6, MPH30: 2}   # HS_NAUX(model): cached per-cell rows (wave bounds; SP also 1/rho and stress row 1)
 HS_SCAL_SLOTS = 8
 
 
@@ -79,10 +80,10 @@ SIGNATURES = {
     "hsd_problem_init": (C.c_int, [C.POINTER(HsdProblem), C.c_int, _eosp, C.c_int, _i64, _i64]),
     "hsd_aos_to_soa": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp]),
     "hsd_soa_to_aos": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp]),
-    "hsd_wave_bounds": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "hsd_wave_bounds": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, C.c_int, _vp]),
     "hsd_step": (C.c_int, [C.POINTER(HsdProblem), C.c_int, C.c_double, C.c_double, C.c_double, _i64,
-                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
-    "hsd_halo": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+                           _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
+    "hsd_halo": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "hsd_scal_lambda_next": (_vp, [_vp, _i64, _i64]),
     "hsd_scal_lambda_cur": (_vp, [_vp, _i64, _i64]),
     "hsd_scal_time": (_vp, [_vp, _i64, _i64]),

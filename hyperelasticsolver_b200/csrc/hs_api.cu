@@ -146,7 +146,7 @@ int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa, double* aos, void*
   return HS_OK;
 }
 
-static int wave_bounds_impl(const hsd_problem_t* p, const double* Q, double* lo, double* hi, double* scal, int slot,
+static int wave_bounds_impl(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot,
                             double* eig_full, cudaStream_t st) {
   if (slot < 0 || slot > 2) return fail(HS_ERR_ARG, "slot must be 0..2");
   unsigned long long* lam = scal_lam(scal) + (size_t)slot * p->nprob;
@@ -158,28 +158,28 @@ static int wave_bounds_impl(const hsd_problem_t* p, const double* Q, double* lo,
   const int tiles = (int)((p->ncells + cpb - 1) / cpb);
   const unsigned nb = (unsigned)(tiles * p->nprob);
   if (p->model == HS_MODEL_MPH30) {
-    if (p->gen) k_bounds<MODEL_MPH30, true, T><<<nb, T, 0, st>>>(Q, lo, hi, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
-    else k_bounds<MODEL_MPH30, false, T><<<nb, T, 0, st>>>(Q, lo, hi, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
+    if (p->gen) k_bounds<MODEL_MPH30, true, T><<<nb, T, 0, st>>>(Q, aux, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
+    else k_bounds<MODEL_MPH30, false, T><<<nb, T, 0, st>>>(Q, aux, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
   } else {
-    if (p->gen) k_bounds<MODEL_SP13, true, T><<<nb, T, 0, st>>>(Q, lo, hi, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
-    else k_bounds<MODEL_SP13, false, T><<<nb, T, 0, st>>>(Q, lo, hi, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
+    if (p->gen) k_bounds<MODEL_SP13, true, T><<<nb, T, 0, st>>>(Q, aux, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
+    else k_bounds<MODEL_SP13, false, T><<<nb, T, 0, st>>>(Q, aux, lam, eig_full, status, p->stride, (int)p->ncells, (int)p->nprob, tiles, e);
   }
   g_launches++;
   CU(cudaGetLastError());
   return HS_OK;
 }
 
-int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* lo, double* hi, double* scal, int slot, void* stream) {
-  return wave_bounds_impl(p, Q, lo, hi, scal, slot, nullptr, (cudaStream_t)stream);
+int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot, void* stream) {
+  return wave_bounds_impl(p, Q, aux, scal, slot, nullptr, (cudaStream_t)stream);
 }
 
 int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
-             const double* lo_in, const double* hi_in, double* Qout, double* lo_out, double* hi_out, double* scal,
+             const double* aux_in, double* Qout, double* aux_out, double* scal,
              double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, void* stream) {
   if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
   if (ghost_mask < 0 || ghost_mask > 3) return fail(HS_ERR_ARG, "ghost_mask must be 0..3");
   StepArgs a;
-  a.Qin = Qin; a.Qout = Qout; a.lo_in = lo_in; a.hi_in = hi_in; a.lo_out = lo_out; a.hi_out = hi_out;
+  a.Qin = Qin; a.Qout = Qout; a.aux_in = aux_in; a.aux_out = aux_out;
   a.lam = scal_lam(scal); a.tt = scal_t(scal, p->nprob); a.steps = scal_steps(scal, p->nprob);
   a.status = scal_status(scal, p->nprob);
   a.dt_hist = dt_hist; a.hist_k = hist_k; a.hist_cap = dt_hist ? hist_cap : 0;
@@ -199,11 +199,11 @@ int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_e
   }
 }
 
-int hsd_halo(const hsd_problem_t* p, double* Q, double* lo, double* hi, double* left, double* right, int mask, int unpack, void* stream) {
+int hsd_halo(const hsd_problem_t* p, double* Q, double* aux, double* left, double* right, int mask, int unpack, void* stream) {
   if (p->nprob != 1) return fail(HS_ERR_ARG, "halo exchange applies to a single slab-decomposed grid");
   if (!mask) return HS_OK;
-  const int nvar = p->model == HS_MODEL_MPH30 ? 30 : 13;
-  k_halo<<<2, 32, 0, (cudaStream_t)stream>>>(Q, lo, hi, left, right, p->stride, (int)p->ncells, nvar, mask, unpack);
+  const int nvar = p->model == HS_MODEL_MPH30 ? 30 : 13, naux = HS_NAUX(p->model);
+  k_halo<<<2, 64, 0, (cudaStream_t)stream>>>(Q, aux, left, right, p->stride, (int)p->ncells, nvar, naux, mask, unpack);
   g_launches++;
   CU(cudaGetLastError());
   return HS_OK;
@@ -224,8 +224,7 @@ struct hs_ctx {
   int nvar;
   cudaStream_t stream;
   double* Q[2];
-  double* lo[2];
-  double* hi[2];
+  double* aux[2];     // [NAUX][stride] cached per-cell rows (wave bounds, ...)
   double* scal;
   double* stage;      // AoS staging, nvar*stride doubles
   double* dt_hist;    // device, grown on demand
@@ -252,12 +251,11 @@ int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase,
   DeviceGuard guard_(device);
   if (!guard_.ok) { delete c; return fail(HS_ERR_CUDA, "cudaSetDevice failed"); }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(HS_ERR_CUDA, "stream creation failed"); }
-  const size_t nq = (size_t)c->nvar * c->prob.stride * sizeof(double), nb = (size_t)c->prob.stride * sizeof(double);
+  const size_t nq = (size_t)c->nvar * c->prob.stride * sizeof(double), nb = (size_t)HS_NAUX(model) * c->prob.stride * sizeof(double);
   cudaError_t e = cudaSuccess;
   for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
     e = cudaMalloc(&c->Q[k], nq);
-    if (e == cudaSuccess) e = cudaMalloc(&c->lo[k], nb);
-    if (e == cudaSuccess) e = cudaMalloc(&c->hi[k], nb);
+    if (e == cudaSuccess) e = cudaMalloc(&c->aux[k], nb);
   }
   if (e == cudaSuccess) e = cudaMalloc(&c->scal, sizeof(double) * HS_SCAL_DOUBLES(nprob));
   if (e == cudaSuccess) e = cudaMemset(c->scal, 0, sizeof(double) * HS_SCAL_DOUBLES(nprob));
@@ -269,7 +267,7 @@ int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase,
 int hs_destroy(hs_ctx_t* c) {
   if (!c) return HS_OK;
   DeviceGuard guard_(c->device);
-  for (int k = 0; k < 2; ++k) { cudaFree(c->Q[k]); cudaFree(c->lo[k]); cudaFree(c->hi[k]); }
+  for (int k = 0; k < 2; ++k) { cudaFree(c->Q[k]); cudaFree(c->aux[k]); }
   cudaFree(c->scal); cudaFree(c->stage); cudaFree(c->dt_hist);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -299,7 +297,7 @@ int hs_upload(hs_ctx_t* c, const double* Q) {
   CU(cudaMemsetAsync(c->scal, 0, sizeof(double) * HS_SCAL_DOUBLES(c->prob.nprob), c->stream));
   c->n = 0;
   rc = hsd_aos_to_soa(&c->prob, c->stage, c->Q[0], c->stream); if (rc) return rc;
-  rc = hsd_wave_bounds(&c->prob, c->Q[0], c->lo[0], c->hi[0], c->scal, 0, c->stream); if (rc) return rc;
+  rc = hsd_wave_bounds(&c->prob, c->Q[0], c->aux[0], c->scal, 0, c->stream); if (rc) return rc;
   return read_status(c);
 }
 
@@ -336,7 +334,7 @@ int hs_wave_speeds(hs_ctx_t* c, double* eig, double* lambda_max) {
     double* d_eig = nullptr;
     CU(cudaMalloc(&d_eig, ne));
     // recompute into the current slot (same values: the sweep is deterministic and max is exact)
-    rc = wave_bounds_impl(&c->prob, c->Q[cur], c->lo[cur], c->hi[cur], c->scal, (int)(c->n % 3), d_eig, c->stream);
+    rc = wave_bounds_impl(&c->prob, c->Q[cur], c->aux[cur], c->scal, (int)(c->n % 3), d_eig, c->stream);
     if (rc == HS_OK && cudaMemcpyAsync(eig, d_eig, ne, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = fail(HS_ERR_CUDA, "eig download failed");
     cudaStreamSynchronize(c->stream);
     cudaFree(d_eig);
@@ -351,7 +349,7 @@ int hs_wave_speeds(hs_ctx_t* c, double* eig, double* lambda_max) {
 
 static int enqueue_step(hs_ctx* c, int flux, double cfl, double dx, double t_end, double* hist, int64_t hist_k, int64_t hist_cap) {
   const int a = (int)(c->n & 1), b = a ^ 1;
-  int rc = hsd_step(&c->prob, flux, cfl, dx, t_end, c->n, c->Q[a], c->lo[a], c->hi[a], c->Q[b], c->lo[b], c->hi[b], c->scal,
+  int rc = hsd_step(&c->prob, flux, cfl, dx, t_end, c->n, c->Q[a], c->aux[a], c->Q[b], c->aux[b], c->scal,
                     hist, hist_k, hist_cap, 0, c->stream);
   if (rc == HS_OK) c->n += 1;
   return rc;

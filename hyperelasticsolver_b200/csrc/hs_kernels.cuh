@@ -21,6 +21,11 @@
 
 namespace hs {
 
+// quadrature nodes evaluated per loop trip of a path integral (tuning knob; 1 = rolled)
+#ifndef HS_NODE_UNROLL
+#define HS_NODE_UNROLL 1
+#endif
+
 constexpr int MODEL_SP13 = 0, MODEL_MPH30 = 1;
 constexpr int FLUX_LXF = 0, FLUX_HLL = 1;
 constexpr unsigned FULL = 0xffffffffu;
@@ -53,8 +58,31 @@ __constant__ double c_glob_w[6] = {0.06666666666666666667 / 2.0, 0.3784749562978
 __host__ __device__ constexpr int sp_slot(int v) { return v < 3 ? 2 + v : (v == 12 ? 5 : 6 + ((v - 3) / 3) + 3 * ((v - 3) % 3)); }
 
 template <int MODEL> struct ModelTraits;
-template <> struct ModelTraits<MODEL_SP13> { static constexpr int NPH = 1, NVAR = 13, J0 = 2; };
-template <> struct ModelTraits<MODEL_MPH30> { static constexpr int NPH = 2, NVAR = 30, J0 = 0; };
+// NAUX: cached per-cell rows next to the state.  Rows 0,1 = wave bounds lo / hi (all any consumer of
+// get_eigvals keeps).  The single-phase model also caches 1/rho and row 1 of the stress (rows 2..5):
+// the CFL sweep at the end of a step computes them anyway, and with them the next step's physical
+// flux needs no state recovery (saves ~20 % of the FP64 work for 32 B/cell more traffic each way).
+template <> struct ModelTraits<MODEL_SP13> { static constexpr int NPH = 1, NVAR = 13, J0 = 2, NAUX = 6; };
+template <> struct ModelTraits<MODEL_MPH30> { static constexpr int NPH = 2, NVAR = 30, J0 = 0, NAUX = 2; };
+
+// physical flux of the single-phase record from the cached 1/rho and stress row (same expressions as
+// phase_flux with alpha = 1; den*u1 is the momentum itself)
+__device__ __forceinline__ void sp_flux_cached(const double* rec, double inv_den, const double* sig1, double* f) {
+  const double* m = rec + 2;
+  const double* A = rec + 6;
+  const double u0 = m[0] * inv_den, u1 = m[1] * inv_den, u2 = m[2] * inv_den;
+  f[2] = m[0] * u0 - sig1[0];
+  f[3] = m[0] * u1 - sig1[1];
+  f[4] = m[0] * u2 - sig1[2];
+  f[5] = m[0] * (rec[5] * inv_den) - (u0 * sig1[0] + u1 * sig1[1] + u2 * sig1[2]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double A1j = A[3 * j];
+    f[6 + 3 * j] = 0.0;
+    f[7 + 3 * j] = u0 * A[1 + 3 * j] - u1 * A1j;
+    f[8 + 3 * j] = u0 * A[2 + 3 * j] - u2 * A1j;
+  }
+}
 
 // state of the record stored in a shared-memory column (row stride T)
 template <int MODEL, bool GEN, int T>
@@ -125,7 +153,8 @@ template <bool GEN, int T>
 __device__ __forceinline__ void path_integral(const EosDev& eos, const double* a, const double* b, const double* xs,
                                               const double* ws, double* acc, int& bad) {
   const double dalpha = b[0] - a[0];
-#pragma unroll 1
+  constexpr int NODE_UNROLL = HS_NODE_UNROLL;
+#pragma unroll NODE_UNROLL
   for (int q = 0; q < 6; ++q) {
     const double s = xs[q], oms = 1.0 - s, w = ws[q] * dalpha;
     const double alpha = a[0] * oms + b[0] * s;
@@ -220,7 +249,7 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
 // ------------------------------------------------------------------------------------------------
 struct StepArgs {
   const double* Qin; double* Qout;
-  const double* lo_in; const double* hi_in; double* lo_out; double* hi_out;
+  const double* aux_in; double* aux_out;   // [NAUX][stride]
   unsigned long long* lam;   // [3][nprob] bit patterns of lambda_max (non-negative doubles order like u64)
   double* tt;                // [3][nprob] time
   long long* steps;          // [nprob]
@@ -272,7 +301,8 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
   // cached bounds) before anything consumes them, so their latencies overlap.
   const unsigned long long lam_bits = __ldg(g.lam + (size_t)g.cur * g.nprob + prob);
   const double t_cur = __ldg(g.tt + (size_t)g.cur * g.nprob + prob);
-  double rin[15], lo_in_r = 0.0, hi_in_r = 0.0;
+  constexpr int NAUX = MT::NAUX;
+  double rin[15], lo_in_r = 0.0, hi_in_r = 0.0, ax[MODEL == MODEL_SP13 ? 4 : 1];
   if (MODEL == MODEL_MPH30) {
 #pragma unroll
     for (int j = 0; j < 15; ++j) rin[j] = __ldg(g.Qin + (size_t)(15 * ph + j) * g.stride + gi);
@@ -280,7 +310,11 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 #pragma unroll
     for (int v = 0; v < 13; ++v) rin[sp_slot(v)] = __ldg(g.Qin + (size_t)v * g.stride + gi);
   }
-  if (ph == 0) { lo_in_r = __ldg(g.lo_in + gi); hi_in_r = __ldg(g.hi_in + gi); }
+  if (ph == 0) { lo_in_r = __ldg(g.aux_in + gi); hi_in_r = __ldg(g.aux_in + g.stride + gi); }
+  if (MODEL == MODEL_SP13) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ax[r] = __ldg(g.aux_in + (size_t)(2 + r) * g.stride + gi);
+  }
 
   const bool own_interior = valid && l >= 1 && l <= CPB - 2 && c <= g.ncells - 2;
   // frozen physical boundary cells, main.jl:219-220 (halo cells of a slab are neither written nor
@@ -308,7 +342,11 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 #pragma unroll
         for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = Rs[sp_slot(v) * T + tid];
       }
-      if (ph == 0) { g.lo_out[gi] = lo_s[l]; g.hi_out[gi] = hi_s[l]; }
+      if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
+      if (MODEL == MODEL_SP13) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g.aux_out[(size_t)(2 + r) * g.stride + gi] = ax[r];
+      }
     }
     if (tile == 0 && tid == 0) {
       g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur;
@@ -319,8 +357,13 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
   }
 
   int bad = 0;
-  // ---- per-cell state and physical flux (flux_mph, HyperelasticityMPh.jl:140-175) -----------
-  {
+  // ---- per-cell physical flux (flux_mph, HyperelasticityMPh.jl:140-175) -----------------------
+  if (MODEL == MODEL_SP13) {
+    double f[15];
+    sp_flux_cached(rin, ax[0], ax + 1, f);   // state recovery was done by the previous step's CFL sweep
+#pragma unroll
+    for (int j = J0; j < 15; ++j) Fs[j * T + tid] = f[j];
+  } else {
     PhaseState st;
     column_state<MODEL, GEN, T>(eos, Rs + tid, st);
     if (valid) bad |= st.bad;
@@ -390,10 +433,19 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     }
     if (own_interior) {
       bad |= sn.bad;
-      if (ph == 0) { g.lo_out[gi] = lo_n; g.hi_out[gi] = hi_n; }
+      if (ph == 0) { g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n; }
+      if (MODEL == MODEL_SP13) {
+        g.aux_out[(size_t)2 * g.stride + gi] = sn.inv_den;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) g.aux_out[(size_t)(3 + r) * g.stride + gi] = sn.sig1[r];
+      }
       lamv = fmax(fabs(lo_n), fabs(hi_n));
     } else if (own_frozen) {
-      if (ph == 0) { g.lo_out[gi] = lo_s[l]; g.hi_out[gi] = hi_s[l]; }
+      if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
+      if (MODEL == MODEL_SP13) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g.aux_out[(size_t)(2 + r) * g.stride + gi] = ax[r];
+      }
       lamv = fmax(fabs(lo_s[l]), fabs(hi_s[l]));
     }
   }
@@ -422,7 +474,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 // optionally the full get_eigvals output (6 per phase) in Julia layout (6*NPH, ncells*nprob).
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, bool GEN, int T>
-__global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, double* __restrict__ lo, double* __restrict__ hi,
+__global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, double* __restrict__ aux,
                                               unsigned long long* lam_slot, double* eig_full, int* status, long long stride,
                                               int ncells, int nprob, int tiles_per_prob, const EosPair eosp) {
   using MT = ModelTraits<MODEL>;
@@ -458,7 +510,12 @@ __global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, doub
   int bad = 0;
   if (valid) {
     bad = st.bad;
-    if (ph == 0) { lo[gi] = lo_c; hi[gi] = hi_c; }
+    if (ph == 0) { aux[gi] = lo_c; aux[stride + gi] = hi_c; }
+    if (MODEL == MODEL_SP13) {
+      aux[(size_t)2 * stride + gi] = st.inv_den;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) aux[(size_t)(3 + r) * stride + gi] = st.sig1[r];
+    }
     lamv = fmax(fabs(lo_c), fabs(hi_c));
     if (eig_full) {  // [u1 + c_k (ascending), u1 - c_k], HyperelasticityMPh.jl:263-265
       double* e = eig_full + (size_t)gi * (6 * NPH) + 6 * ph;
@@ -521,18 +578,18 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(const double* __restrict__ s
   }
 }
 
-// Halo pack / unpack for the slab decomposition: buf = [Q(nvar), lo, hi] of one cell.
+// Halo pack / unpack for the slab decomposition: buf = [Q(nvar), aux(naux)] of one cell.
 // pack: first owned cell (index 1) -> to_left, last owned (ncells-2) -> to_right.
 // unpack: from_left -> cell 0, from_right -> cell ncells-1.   mask bit 0 / 1 = left / right neighbour exists.
-__global__ void k_halo(double* Q, double* lo, double* hi, double* left, double* right, long long stride, int ncells, int nvar,
+__global__ void k_halo(double* Q, double* aux, double* left, double* right, long long stride, int ncells, int nvar, int naux,
                        int mask, int unpack) {
   const int v = threadIdx.x;
-  if (v >= nvar + 2) return;
+  if (v >= nvar + naux) return;
   const int side = blockIdx.x;   // 0 left, 1 right
   if (!(mask & (1 << side))) return;
   double* buf = side ? right : left;
   const long long cell = unpack ? (side ? ncells - 1 : 0) : (side ? ncells - 2 : 1);
-  double* p = v < nvar ? Q + (size_t)v * stride + cell : (v == nvar ? lo + cell : hi + cell);
+  double* p = v < nvar ? Q + (size_t)v * stride + cell : aux + (size_t)(v - nvar) * stride + cell;
   if (unpack) *p = buf[v]; else buf[v] = *p;
 }
 

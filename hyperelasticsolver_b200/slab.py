@@ -8,7 +8,7 @@ All arithmetic runs in libhyperelastic_b200.so through the device-pointer layer 
 
 Per step and per rank:
     hsd_step                         fused kernel (reads lambda_max slot n%3, writes slot (n+1)%3)
-    halo exchange                    first / last owned cell (nvar + 2 doubles) to the neighbours
+    halo exchange                    first / last owned cell (nvar + HS_NAUX doubles) to the neighbours
     all_reduce(MAX) of slot (n+1)%3  -> dt of the next step is bit-identical on all ranks and
                                         identical to the single-GPU run (max is exact)
 Both collectives are enqueued on the same stream as the kernels: no host synchronisation.
@@ -44,6 +44,7 @@ class CudaKernels:
     def __init__(self, eos, model, device):
         self.model = model
         self.nvar = L.NVAR[model]
+        self.naux = L.NAUX[model]
         self.device = torch.device(device)
         self._eos = L.eos_array(eos, model)
         self._lib = L.lib()
@@ -70,16 +71,16 @@ class CudaKernels:
     def soa_to_aos(self, prob, soa, aos):
         L.check(self._lib.hsd_soa_to_aos(C.byref(prob), soa.data_ptr(), aos.data_ptr(), self._stream()))
 
-    def wave_bounds(self, prob, Q, lo, hi, scal, slot):
-        L.check(self._lib.hsd_wave_bounds(C.byref(prob), Q.data_ptr(), lo.data_ptr(), hi.data_ptr(), scal.data_ptr(), slot, self._stream()))
+    def wave_bounds(self, prob, Q, aux, scal, slot):
+        L.check(self._lib.hsd_wave_bounds(C.byref(prob), Q.data_ptr(), aux.data_ptr(), scal.data_ptr(), slot, self._stream()))
 
-    def step(self, prob, flux, cfl, dx, t_end, n, Qin, lo_in, hi_in, Qout, lo_out, hi_out, scal, ghost_mask, dt_hist=None, hist_k=0, hist_cap=0):
-        L.check(self._lib.hsd_step(C.byref(prob), flux, cfl, dx, t_end, n, Qin.data_ptr(), lo_in.data_ptr(), hi_in.data_ptr(),
-                                   Qout.data_ptr(), lo_out.data_ptr(), hi_out.data_ptr(), scal.data_ptr(),
+    def step(self, prob, flux, cfl, dx, t_end, n, Qin, aux_in, Qout, aux_out, scal, ghost_mask, dt_hist=None, hist_k=0, hist_cap=0):
+        L.check(self._lib.hsd_step(C.byref(prob), flux, cfl, dx, t_end, n, Qin.data_ptr(), aux_in.data_ptr(),
+                                   Qout.data_ptr(), aux_out.data_ptr(), scal.data_ptr(),
                                    dt_hist.data_ptr() if dt_hist is not None else None, hist_k, hist_cap, ghost_mask, self._stream()))
 
-    def halo(self, prob, Q, lo, hi, left, right, mask, unpack):
-        L.check(self._lib.hsd_halo(C.byref(prob), Q.data_ptr(), lo.data_ptr(), hi.data_ptr(), left.data_ptr(), right.data_ptr(),
+    def halo(self, prob, Q, aux, left, right, mask, unpack):
+        L.check(self._lib.hsd_halo(C.byref(prob), Q.data_ptr(), aux.data_ptr(), left.data_ptr(), right.data_ptr(),
                                    mask, int(unpack), self._stream()))
 
     def launches(self):
@@ -134,12 +135,11 @@ class SlabSolver(_Base):
         self.ghost_mask = (1 if self.rank > 0 else 0) | (2 if self.rank < self.world - 1 else 0)
         self.prob = kernels.problem(self.nloc, 1)
         self.Q = [kernels.empty(self.nvar, self.nloc) for _ in range(2)]
-        self.lo = [kernels.empty(self.nloc) for _ in range(2)]
-        self.hi = [kernels.empty(self.nloc) for _ in range(2)]
+        self.aux = [kernels.empty(kernels.naux, self.nloc) for _ in range(2)]   # cached per-cell rows (wave bounds, ...)
         self.scal = kernels.zeros(scal_size(1))
         self._views()
         self.n = 0
-        w = self.nvar + 2
+        w = self.nvar + kernels.naux
         self._send = [kernels.empty(w), kernels.empty(w)]   # to left, to right
         self._recv = [kernels.empty(w), kernels.empty(w)]   # from left, from right
 
@@ -155,7 +155,7 @@ class SlabSolver(_Base):
         self.scal.zero_()
         self.n = 0
         self.k.aos_to_soa(self.prob, aos, self.Q[0])
-        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self.k.wave_bounds(self.prob, self.Q[0], self.aux[0], self.scal, 0)
         self._allreduce_lambda(0)
         if check:
             self.check_status()
@@ -164,7 +164,7 @@ class SlabSolver(_Base):
         """Q[0] was filled in place (structure of arrays): reset the clock and run the CFL sweep."""
         self.scal.zero_()
         self.n = 0
-        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self.k.wave_bounds(self.prob, self.Q[0], self.aux[0], self.scal, 0)
         self._allreduce_lambda(0)
         self.check_status()
 
@@ -216,8 +216,8 @@ class SlabSolver(_Base):
     def _halo_exchange(self, buf):
         if self.world == 1:
             return
-        Q, lo, hi = self.Q[buf], self.lo[buf], self.hi[buf]
-        self.k.halo(self.prob, Q, lo, hi, self._send[0], self._send[1], self.ghost_mask, False)
+        Q, aux = self.Q[buf], self.aux[buf]
+        self.k.halo(self.prob, Q, aux, self._send[0], self._send[1], self.ghost_mask, False)
         ops = []
         if self.rank > 0:
             ops += [dist.P2POp(dist.isend, self._send[0], self.rank - 1, self.group), dist.P2POp(dist.irecv, self._recv[0], self.rank - 1, self.group)]
@@ -225,7 +225,7 @@ class SlabSolver(_Base):
             ops += [dist.P2POp(dist.isend, self._send[1], self.rank + 1, self.group), dist.P2POp(dist.irecv, self._recv[1], self.rank + 1, self.group)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        self.k.halo(self.prob, Q, lo, hi, self._recv[0], self._recv[1], self.ghost_mask, True)
+        self.k.halo(self.prob, Q, aux, self._recv[0], self._recv[1], self.ghost_mask, True)
 
     # -- the loop -------------------------------------------------------------------------------
     def step(self, flux=L.HLL, cfl=0.6, dx=None, t_end=1.0e300, kernel_events=None):
@@ -233,8 +233,7 @@ class SlabSolver(_Base):
         a, b = self.n & 1, (self.n & 1) ^ 1
         if kernel_events:
             kernel_events[0].record()
-        self.k.step(self.prob, flux, cfl, dx, t_end, self.n, self.Q[a], self.lo[a], self.hi[a], self.Q[b], self.lo[b], self.hi[b],
-                    self.scal, self.ghost_mask)
+        self.k.step(self.prob, flux, cfl, dx, t_end, self.n, self.Q[a], self.aux[a], self.Q[b], self.aux[b], self.scal, self.ghost_mask)
         if kernel_events:
             kernel_events[1].record()
         self._halo_exchange(b)
@@ -269,8 +268,7 @@ class EnsembleSolver(_Base):
         self.prob = kernels.problem(self.ncells, self.nprob)
         tot = self.ncells * self.nprob
         self.Q = [kernels.empty(self.nvar, tot) for _ in range(2)]
-        self.lo = [kernels.empty(tot) for _ in range(2)]
-        self.hi = [kernels.empty(tot) for _ in range(2)]
+        self.aux = [kernels.empty(kernels.naux, tot) for _ in range(2)]
         self.scal = kernels.zeros(scal_size(self.nprob))
         self._views()
         self.n = 0
@@ -285,13 +283,13 @@ class EnsembleSolver(_Base):
         self.scal.zero_()
         self.n = 0
         self.k.aos_to_soa(self.prob, aos, self.Q[0])
-        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self.k.wave_bounds(self.prob, self.Q[0], self.aux[0], self.scal, 0)
         self.check_status()
 
     def init_from_soa(self):
         self.scal.zero_()
         self.n = 0
-        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self.k.wave_bounds(self.prob, self.Q[0], self.aux[0], self.scal, 0)
         self.check_status()
 
     def local(self):
@@ -309,7 +307,7 @@ class EnsembleSolver(_Base):
         self.scal.zero_()
         self.n = 0
         self.k.aos_to_soa(self.prob, self._stage, self.Q[0])
-        self.k.wave_bounds(self.prob, self.Q[0], self.lo[0], self.hi[0], self.scal, 0)
+        self.k.wave_bounds(self.prob, self.Q[0], self.aux[0], self.scal, 0)
         self.step(flux, cfl, dx)
         self.k.soa_to_aos(self.prob, self.Q[self.n & 1], self._stage)
         host_out.copy_(self._stage, non_blocking=True)
@@ -320,8 +318,7 @@ class EnsembleSolver(_Base):
         a, b = self.n & 1, (self.n & 1) ^ 1
         if kernel_events:
             kernel_events[0].record()
-        self.k.step(self.prob, flux, cfl, dx, t_end, self.n, self.Q[a], self.lo[a], self.hi[a], self.Q[b], self.lo[b], self.hi[b],
-                    self.scal, 0)
+        self.k.step(self.prob, flux, cfl, dx, t_end, self.n, self.Q[a], self.aux[a], self.Q[b], self.aux[b], self.scal, 0)
         if kernel_events:
             kernel_events[1].record()
         self.n += 1

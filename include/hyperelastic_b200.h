@@ -118,10 +118,13 @@ int hs_lxf(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, 
  * one-process-per-GPU driver uses so that halo exchange / allreduce (NCCL through
  * torch.distributed) can be enqueued on the same stream between steps.
  *   Q      : [nvar][stride] doubles, stride = ncells*nprob (cell index = prob*ncells + i)
- *   lo, hi : [stride] cached per-cell wave bounds min/max over phases of u1 -+ c_max
+ *   aux    : [HS_NAUX(model)][stride] cached per-cell rows: 0/1 = wave bounds min/max over phases of
+ *            u1 -+ c_max; single-phase rows 2..5 = 1/rho and row 1 of the stress (what the next
+ *            step's physical flux needs, so it can skip the state recovery)
  *   scal   : HS_SCAL_DOUBLES(nprob) doubles of per-problem scalars (lambda_max x3 slots, t x3
  *            slots, step count, status); opaque, zero-initialise, see hsd_scal_* helpers
  * ------------------------------------------------------------------------------------------ */
+#define HS_NAUX(model) ((model) == HS_MODEL_SP13 ? 6 : 2)
 #define HS_SCAL_SLOTS 8
 #define HS_SCAL_DOUBLES(nprob) (HS_SCAL_SLOTS * (nprob) + 8)
 
@@ -137,20 +140,20 @@ int hsd_problem_init(hsd_problem_t* prob_out, int model, const hs_barton2009_t* 
 /* AoS (nvar, n) <-> SoA [nvar][stride] on the device */
 int hsd_aos_to_soa(const hsd_problem_t* p, const double* aos_dev, double* soa_dev, void* stream);
 int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa_dev, double* aos_dev, void* stream);
-/* CFL sweep: fills lo, hi and lambda_max slot `slot` of scal (after zeroing it) */
-int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* lo, double* hi, double* scal, int slot, void* stream);
-/* one fused step n: reads Qin/lo_in/hi_in and slot n%3, writes Qout/lo_out/hi_out and slot (n+1)%3;
+/* CFL sweep: fills aux and lambda_max slot `slot` of scal (after zeroing it) */
+int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot, void* stream);
+/* one fused step n: reads Qin/aux_in and slot n%3, writes Qout/aux_out and slot (n+1)%3;
  * if dt_hist != NULL the step's dt of problem p is stored at dt_hist[p*hist_cap + hist_k].
  * ghost_mask bit 0 / bit 1: the first / last cell of the array is a halo copy of a neighbouring
  * slab's cell (not written, not counted in lambda_max) instead of a frozen physical boundary cell
  * (main.jl:219-220). */
 int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n,
-             const double* Qin, const double* lo_in, const double* hi_in, double* Qout, double* lo_out, double* hi_out,
+             const double* Qin, const double* aux_in, double* Qout, double* aux_out,
              double* scal, double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, void* stream);
-/* halo of a slab (nprob == 1): unpack == 0 packs [Q(nvar), lo, hi] of the first / last OWNED cell
- * (index 1 / ncells-2) into left / right (nvar+2 doubles each); unpack == 1 stores left / right into
- * the halo cells (index 0 / ncells-1).  mask bit 0 / 1: a left / right neighbour exists. */
-int hsd_halo(const hsd_problem_t* p, double* Q, double* lo, double* hi, double* left, double* right, int mask, int unpack, void* stream);
+/* halo of a slab (nprob == 1): unpack == 0 packs [Q(nvar), aux(HS_NAUX)] of the first / last OWNED
+ * cell (index 1 / ncells-2) into left / right (nvar+HS_NAUX doubles each); unpack == 1 stores left /
+ * right into the halo cells (index 0 / ncells-1).  mask bit 0 / 1: a left / right neighbour exists. */
+int hsd_halo(const hsd_problem_t* p, double* Q, double* aux, double* left, double* right, int mask, int unpack, void* stream);
 /* address (device pointer) of the lambda_max slot that step n WRITES, as doubles [nprob]:
  * the buffer to all-reduce(max) across ranks between step n and n+1 */
 double* hsd_scal_lambda_next(double* scal, int64_t nprob, int64_t n);

@@ -14,6 +14,7 @@ class OracleKernels:
     def __init__(self, eos_blocks, model):
         self.model = model
         self.nvar = O.NVAR[model]
+        self.naux = 6 if model == O.SP13 else 2   # rows 0,1 = lo, hi; the rest is carried but unused by the double
         self.neig = O.NEIG[model]
         self.eos = eos_blocks
         self.device = torch.device("cpu")
@@ -36,33 +37,35 @@ class OracleKernels:
     def launches(self):
         return self._launches
 
-    def halo(self, prob, Q, lo, hi, left, right, mask, unpack):
+    def halo(self, prob, Q, aux, left, right, mask, unpack):
         nv, last = self.nvar, Q.shape[1] - 1
         for side, buf in ((0, left), (1, right)):
             if not (mask & (1 << side)):
                 continue
             if unpack:
                 c = last if side else 0
-                Q[:, c] = buf[:nv]; lo[c] = buf[nv]; hi[c] = buf[nv + 1]
+                Q[:, c] = buf[:nv]; aux[:, c] = buf[nv:]
             else:
                 c = last - 1 if side else 1
-                buf[:nv] = Q[:, c]; buf[nv] = lo[c]; buf[nv + 1] = hi[c]
+                buf[:nv] = Q[:, c]; buf[nv:] = aux[:, c]
 
     def _bounds(self, Qaos):
         eig, st = O.get_eigvals(self.eos, self.model, Qaos)
         assert st == 0
         return eig.min(axis=1), eig.max(axis=1), eig
 
-    def wave_bounds(self, prob, Q, lo, hi, scal, slot):
+    def wave_bounds(self, prob, Q, aux, scal, slot):
         assert prob.nprob == 1
+        lo, hi = aux[0], aux[1]
         l, h, _ = self._bounds(Q.numpy().T.copy())
         lo.copy_(torch.from_numpy(l)); hi.copy_(torch.from_numpy(h))
         scal[slot] = float(np.maximum(np.abs(l), np.abs(h)).max())
         self._launches += 1
 
-    def step(self, prob, flux, cfl, dx, t_end, n, Qin, lo_in, hi_in, Qout, lo_out, hi_out, scal, ghost_mask, **kw):
+    def step(self, prob, flux, cfl, dx, t_end, n, Qin, aux_in, Qout, aux_out, scal, ghost_mask, **kw):
         """main.jl:212-227 on the local array; first / last cell frozen or ghost."""
         assert prob.nprob == 1
+        lo_in, hi_in, lo_out, hi_out = aux_in[0], aux_in[1], aux_out[0], aux_out[1]
         cur, nxt, clr = n % 3, (n + 1) % 3, (n + 2) % 3
         t_cur = float(scal[3 + cur])
         lam = float(scal[cur])
