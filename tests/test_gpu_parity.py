@@ -225,3 +225,56 @@ def test_driver_default_run_matches_oracle(gpu, oracle, tmp_path):
     x = (np.arange(1, nx + 1) - 0.5) / nx
     assert np.allclose(Q0[:, 0], 0.1 * (np.tanh(4 * (x - 0.5) / 0.2) + 1) + 0.4, rtol=1e-15)
     assert np.allclose(Q0[:, 0] + Q0[:, 15], 1.0, rtol=0, atol=1e-16)
+
+
+def test_config0_default_run_641_steps(gpu, oracle):
+    """BASELINE config 0 = main.jl as shipped: two-phase, test case 6, nx = 1000, cfl 0.6, T = 0.06,
+    HLL.  SURVEY.md B.6: 641 steps, t_end = 0.06003958139325407; parity <= 1e-9 after N steps."""
+    import json, os
+    hs = gpu
+    B = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_appendix_b.json")))["default_run"]
+    eos = (hs.Barton2009(), hs.Barton2009())
+    nx, T = 1000, 0.06
+    Ql, Qr = hs.initial_states(eos, 6)
+    Q0 = hs.initial_condition(Ql, Qr, nx)
+    with hs.Solver(eos, nx) as sol:
+        sol.upload(Q0)
+        hist = sol.advance(T, "hll", 0.6, 1.0 / nx, max_steps=1000, record_dt=True)
+        Q = sol.download()
+        steps, t = int(sol.steps[0]), float(sol.t[0])
+    assert steps == B["steps"] == 641
+    assert abs(t - B["t_end"]) < 1e-12 * t
+    dts = hist[0, :steps]
+    assert abs(dts.min() - B["dt_min"]) < 1e-11 * B["dt_min"] and abs(dts.max() - B["dt_max"]) < 1e-11 * B["dt_max"]
+    assert abs(dts[-1] - B["dt_last"]) < 1e-10 * B["dt_last"]
+    assert np.allclose(Q[500, :6], B["cell501_Q_1_6"], rtol=1e-10)
+    assert Q[:, 0].min() >= 0.1 - 1e-12 and Q[:, 0].max() <= 0.9 + 1e-12 and np.abs(Q[:, 0] + Q[:, 15] - 1).max() < 1e-14
+    ref = oracle.run(None, oracle.MPH30, oracle.HLL, Q0, 0.6, 1.0 / nx, T, 1000, nthreads=oracle.hardware_threads())
+    assert ref["steps"][0] == 641 and relerr(Q, ref["Q"]) < 1e-9
+    assert np.allclose(dts, ref["dt"][0, :641], rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("model", ["mph30", "sp13"])
+def test_config4_ensemble_sample_of_64(gpu, oracle, model):
+    """BASELINE config 4 in miniature with its own generator (bench.ensemble_states): 64 random
+    problems validated end to end against the oracle, per-problem dt."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from hyperelasticsolver_b200.slab import CudaKernels, EnsembleSolver
+    hs = gpu
+    nprob, nx, nsteps = 64, 192, 16
+    eos, hmodel, Qlr = bench.ensemble_states(hs, model, 1000, 1000 + nprob)     # problems 1000..1063 of the 65,536
+    om = oracle.MPH30 if model == "mph30" else oracle.SP13
+    oe = [oracle.barton2009()] * (2 if model == "mph30" else 1)
+    Q0 = np.stack([hs.initial_condition(Qlr[i, 0], Qlr[i, 1], nx) for i in range(nprob)])
+    sol = EnsembleSolver(CudaKernels(eos, hmodel, "cuda:0"), nx, nprob)
+    sol.set_local(Q0)
+    for _ in range(nsteps):
+        sol.step(hs.HLL, 0.6, 1.0 / nx)
+    sol.check_status()
+    ref = oracle.run(oe, om, oracle.HLL, Q0, 0.6, 1.0 / nx, 1e9, nsteps, nthreads=oracle.hardware_threads())
+    assert ref["status"] == 0                                  # admissibility of the generator's states
+    nv = Q0.shape[-1]
+    assert relerr(sol.local().reshape(-1, nv), ref["Q"].reshape(-1, nv)) < 1e-9
+    assert np.allclose(sol.t, ref["t"], rtol=1e-11) and len(set(np.round(sol.t, 12))) > 32    # genuinely different dt per problem
