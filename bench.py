@@ -221,6 +221,7 @@ def run_ours(args):
                 Q0[v].view(nprob_local, -1)[:] = torch.where(left_mask_cells[None, :], ql[:, v, None], qr[:, v, None])
         sol_.init_from_soa()
 
+    exchange_kind = "none"
     if ensemble:
         nprob_g, ncells = wl["nprob"], wl["cells"]
         p0, p1 = nprob_g * rank // world, nprob_g * (rank + 1) // world
@@ -243,6 +244,7 @@ def run_ours(args):
         fill_riemann_soa(sol, torch.as_tensor(Ql, device=dev), torch.as_tensor(Qr, device=dev), gidx < n_global / 2)
         del gidx
         n_units = n_global
+        exchange_kind = {"nccl": "NCCL send/recv + all-reduce", "p2p-kernel": "one peer-memory kernel over NVLink (hsd_exchange_p2p)"}[sol.exchange] if world > 1 else "nothing (1 GPU)"
         local_cells = sol.nloc
         dx = 1.0 / n_global
         updated_local = sol.nloc - 2
@@ -371,7 +373,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": wl["desc"], "model": None, "flux": "hll", "cfl": 0.6,
                        "cells_total": n_units, "cells_per_gpu": local_cells,
-                       "parallelism": ("ensemble partition, no collective" if ensemble else f"slab x{world}, halo send/recv + allreduce(max) per step"),
+                       "parallelism": ("ensemble partition, no collective" if ensemble else f"slab x{world}, halo + max(lambda) per step via {exchange_kind}"),
                        "l2": f"state {local_cells * nvar * 8 / 1e9:.2f} GB per GPU per buffer >> 126 MB L2 (inputs larger than L2, no flush needed)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }

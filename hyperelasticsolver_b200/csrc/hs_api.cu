@@ -209,6 +209,24 @@ int hsd_halo(const hsd_problem_t* p, double* Q, double* aux, double* left, doubl
   return HS_OK;
 }
 
+int hsd_mailbox_doubles(void) { return 2 * MBOX_STRIDE; }
+
+int hsd_exchange_p2p(const hsd_problem_t* p, double* Q, double* aux, double* lam_slot, void* const* mailboxes, int rank, int world,
+                     uint64_t seq, void* stream) {
+  if (p->nprob != 1) return fail(HS_ERR_ARG, "halo exchange applies to a single slab-decomposed grid");
+  if (world < 1 || world > MBOX_MAXR || rank < 0 || rank >= world) return fail(HS_ERR_ARG, "p2p exchange supports 1..8 ranks on one node");
+  if (seq == 0) return fail(HS_ERR_ARG, "seq must start at 1 (mailboxes are zero-initialised)");
+  const int nvar = p->model == HS_MODEL_MPH30 ? 30 : 13, naux = HS_NAUX(p->model);
+  if (nvar + naux > MBOX_MAXW) return fail(HS_ERR_ARG, "mailbox too small");
+  PeerPtrs pp;
+  for (int i = 0; i < MBOX_MAXR; ++i) pp.p[i] = i < world ? static_cast<double*>(mailboxes[i]) : nullptr;
+  k_exchange_p2p<<<1, 64, 0, (cudaStream_t)stream>>>(Q, aux, reinterpret_cast<unsigned long long*>(lam_slot), pp, p->stride,
+                                                    (int)p->ncells, nvar, naux, rank, world, (unsigned long long)seq);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+
 double* hsd_scal_lambda_next(double* scal, int64_t nprob, int64_t n) { return scal + ((n + 1) % 3) * nprob; }
 double* hsd_scal_lambda_cur(double* scal, int64_t nprob, int64_t n) { return scal + (n % 3) * nprob; }
 double* hsd_scal_time(double* scal, int64_t nprob, int64_t n) { return scal + 3 * nprob + (n % 3) * nprob; }

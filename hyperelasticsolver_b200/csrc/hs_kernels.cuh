@@ -594,6 +594,64 @@ __global__ void k_halo(double* Q, double* aux, double* left, double* right, long
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_exchange_p2p: the per-step exchange of a slab-decomposed grid in ONE small kernel over NVLink
+// peer memory (no NCCL call on the step path).  Every rank owns a mailbox in symmetric memory that
+// all peers can address:
+//   mbox[parity] = { from_left[W], from_right[W], lam[8], flag[8] }     W = nvar + naux, parity = seq & 1
+// post:   my first / last owned cell -> the neighbours' from_right / from_left, my local lambda_max
+//         -> lam[rank] of EVERY peer, __threadfence_system(), then flag[rank] = seq on every peer;
+// wait:   spin until flag[p] == seq for every peer p of my own mailbox;
+// unpack: halo cells <- from_left / from_right, lambda_max slot <- max_p lam[p].
+// max is exact and nothing else crosses ranks, so the result is bit-identical to the NCCL path and to
+// the single-GPU run.  Two parities suffice: a rank can only post step n+1 after every peer has
+// posted step n (it waited for their flags), and no peer can post step n+2 before it has my n+1 flag.
+// ------------------------------------------------------------------------------------------------
+constexpr int MBOX_MAXW = 40, MBOX_MAXR = 8;
+constexpr int MBOX_STRIDE = 2 * MBOX_MAXW + 2 * MBOX_MAXR;    // doubles per parity
+struct PeerPtrs { double* p[MBOX_MAXR]; };
+
+__global__ void __launch_bounds__(64) k_exchange_p2p(double* Q, double* aux, unsigned long long* lam_slot, const PeerPtrs peers,
+                                                     long long stride, int ncells, int nvar, int naux, int rank, int world,
+                                                     unsigned long long seq) {
+  const int v = threadIdx.x, W = nvar + naux;
+  const int par = (int)(seq & 1ull);
+  const size_t base = (size_t)par * MBOX_STRIDE;
+  // ---- post ---------------------------------------------------------------------------------
+  if (v < W) {
+    const double* src = v < nvar ? Q + (size_t)v * stride : aux + (size_t)(v - nvar) * stride;
+    if (rank > 0) peers.p[rank - 1][base + MBOX_MAXW + v] = src[1];                  // my first owned cell -> left peer's from_right
+    if (rank < world - 1) peers.p[rank + 1][base + v] = src[ncells - 2];             // my last owned cell -> right peer's from_left
+  }
+  if (v < world) reinterpret_cast<unsigned long long*>(peers.p[v] + base + 2 * MBOX_MAXW)[rank] = *lam_slot;
+  __threadfence_system();
+  __syncthreads();
+  if (v < world) {
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers.p[v] + base + 2 * MBOX_MAXW + MBOX_MAXR);
+    f[rank] = seq;
+  }
+  // ---- wait ---------------------------------------------------------------------------------
+  double* mine = peers.p[rank] + base;
+  if (v < world) {
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(mine + 2 * MBOX_MAXW + MBOX_MAXR);
+    while (f[v] != seq) { }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // ---- unpack -------------------------------------------------------------------------------
+  if (v < W) {
+    double* dst = v < nvar ? Q + (size_t)v * stride : aux + (size_t)(v - nvar) * stride;
+    if (rank > 0) dst[0] = __ldcv(mine + v);
+    if (rank < world - 1) dst[ncells - 1] = __ldcv(mine + MBOX_MAXW + v);
+  }
+  if (v == 0) {
+    const unsigned long long* l = reinterpret_cast<const unsigned long long*>(mine + 2 * MBOX_MAXW);
+    unsigned long long m = 0ull;
+    for (int p = 0; p < world; ++p) { const unsigned long long x = __ldcv(l + p); m = x > m ? x : m; }
+    *lam_slot = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stateless batches over Julia-layout arrays: literal drop-ins for the per-cell / per-face
 // reference functions.  One thread per (item, phase).
 // ------------------------------------------------------------------------------------------------

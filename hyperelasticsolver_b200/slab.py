@@ -83,6 +83,14 @@ class CudaKernels:
         L.check(self._lib.hsd_halo(C.byref(prob), Q.data_ptr(), aux.data_ptr(), left.data_ptr(), right.data_ptr(),
                                    mask, int(unpack), self._stream()))
 
+    def mailbox_doubles(self):
+        return int(self._lib.hsd_mailbox_doubles())
+
+    def exchange_p2p(self, prob, Q, aux, lam_slot, peer_ptrs, rank, world, seq):
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in peer_ptrs])
+        L.check(self._lib.hsd_exchange_p2p(C.byref(prob), Q.data_ptr(), aux.data_ptr(), lam_slot.data_ptr(), arr, rank, world, seq,
+                                           self._stream()))
+
     def launches(self):
         return int(self._lib.hs_kernel_launch_count())
 
@@ -142,6 +150,33 @@ class SlabSolver(_Base):
         w = self.nvar + kernels.naux
         self._send = [kernels.empty(w), kernels.empty(w)]   # to left, to right
         self._recv = [kernels.empty(w), kernels.empty(w)]   # from left, from right
+        self.exchange = "nccl"      # halo send/recv + all-reduce(max) through torch.distributed
+        self._xseq = 0
+        self._setup_p2p()
+
+    def _setup_p2p(self):
+        """One-kernel exchange over NVLink peer memory (hsd_exchange_p2p): mailboxes in symmetric memory.
+        Falls back to the NCCL path when symmetric memory is unavailable (gloo, > 8 ranks, HS_EXCHANGE=nccl)."""
+        import os
+        if self.world == 1 or self.world > 8 or os.environ.get("HS_EXCHANGE", "p2p") != "p2p" or not hasattr(self.k, "exchange_p2p"):
+            return
+        if self.k.device.type != "cuda" or dist.get_backend(self.group) != "nccl":
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            self._mbox = symm.empty(self.k.mailbox_doubles(), dtype=torch.float64, device=self.k.device)
+            self._mbox.zero_()
+            hdl = symm.rendezvous(self._mbox, self.group if self.group is not None else dist.group.WORLD)
+            self._peer_ptrs = [int(x) for x in hdl.buffer_ptrs]
+            torch.cuda.synchronize(self.k.device)
+            dist.barrier(group=self.group)       # every mailbox is zeroed before anybody posts
+            ok = torch.ones(1, device=self.k.device)
+        except Exception as e:                    # noqa: BLE001 -- any failure means "use NCCL"
+            self._p2p_error = repr(e)
+            ok = torch.zeros(1, device=self.k.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)   # all ranks must agree on the path
+        if float(ok.item()) == 1.0:
+            self.exchange = "p2p-kernel"
 
     # -- state ----------------------------------------------------------------------------------
     def set_local(self, Q_local):
@@ -236,8 +271,13 @@ class SlabSolver(_Base):
         self.k.step(self.prob, flux, cfl, dx, t_end, self.n, self.Q[a], self.aux[a], self.Q[b], self.aux[b], self.scal, self.ghost_mask)
         if kernel_events:
             kernel_events[1].record()
-        self._halo_exchange(b)
-        self._allreduce_lambda((self.n + 1) % 3)
+        if self.exchange == "p2p-kernel":
+            self._xseq += 1
+            self.k.exchange_p2p(self.prob, self.Q[b], self.aux[b], self._lam[(self.n + 1) % 3], self._peer_ptrs, self.rank, self.world,
+                                self._xseq)
+        else:
+            self._halo_exchange(b)
+            self._allreduce_lambda((self.n + 1) % 3)
         self.n += 1
 
     def advance(self, t_end, flux=L.HLL, cfl=0.6, dx=None, max_steps=1 << 30, check_every=32):

@@ -154,6 +154,15 @@ int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_e
  * cell (index 1 / ncells-2) into left / right (nvar+HS_NAUX doubles each); unpack == 1 stores left /
  * right into the halo cells (index 0 / ncells-1).  mask bit 0 / 1: a left / right neighbour exists. */
 int hsd_halo(const hsd_problem_t* p, double* Q, double* aux, double* left, double* right, int mask, int unpack, void* stream);
+/* The same exchange plus the max-reduction of lambda_max in ONE kernel over NVLink peer memory (no NCCL
+ * on the step path).  mailboxes[world]: device pointers, valid in THIS process, of every rank's mailbox
+ * (hsd_mailbox_doubles() doubles each, zero-initialised, allocated as peer-accessible / symmetric
+ * memory, e.g. torch.distributed._symmetric_memory); lam_slot = hsd_scal_lambda_next(scal, 1, n) of the
+ * step just enqueued; seq = 1, 2, 3, ... identical on all ranks and never reused.  <= 8 ranks, one node.
+ * Results are bit-identical to hsd_halo + all-reduce(max). */
+int hsd_mailbox_doubles(void);
+int hsd_exchange_p2p(const hsd_problem_t* p, double* Q, double* aux, double* lam_slot, void* const* mailboxes, int rank, int world,
+                     uint64_t seq, void* stream);
 /* address (device pointer) of the lambda_max slot that step n WRITES, as doubles [nprob]:
  * the buffer to all-reduce(max) across ranks between step n and n+1 */
 double* hsd_scal_lambda_next(double* scal, int64_t nprob, int64_t n);

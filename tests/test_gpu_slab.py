@@ -75,7 +75,8 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _nccl_worker(rank, world, port, nx, nsteps, q):
+def _nccl_worker(rank, world, port, nx, nsteps, q, exchange="p2p"):
+    os.environ["HS_EXCHANGE"] = exchange
     sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     import torch
@@ -96,14 +97,16 @@ def _nccl_worker(rank, world, port, nx, nsteps, q):
         if rank == 0:
             with hs.Solver(eos, nx, model=hs.SP13, device=0) as s1:
                 s1.upload(Q0); s1.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=nsteps)
-                q.put((np.array_equal(s1.download(), Q), float(s1.t[0]), float(sol.t[0])))
+                q.put((np.array_equal(s1.download(), Q), float(s1.t[0]), float(sol.t[0]), sol.exchange, getattr(sol, "_p2p_error", "")))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpu_slab_bit_identical(gpu):
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_slab_bit_identical(gpu, exchange):
     """2^n-independent check of BASELINE config 3's requirement: the slab-decomposed run is
-    bit-identical to the single-GPU run (only an exact max crosses ranks)."""
+    bit-identical to the single-GPU run (only an exact max crosses ranks) -- with the one-kernel
+    peer-memory exchange and with the NCCL exchange."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -111,12 +114,13 @@ def test_two_gpu_slab_bit_identical(gpu):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, 5000, 25, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, 5000, 25, q, exchange)) for r in range(2)]
     for p in procs: p.start()
-    same, t1, t2 = q.get(timeout=300)
+    same, t1, t2, kind, err = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120); assert p.exitcode == 0
     assert same and t1 == t2
+    assert kind == ("p2p-kernel" if exchange == "p2p" else "nccl"), f"exchange path {kind}: {err}"
 
 
 def test_stateless_calls_keep_current_device(gpu):
