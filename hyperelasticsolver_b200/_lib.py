@@ -74,7 +74,7 @@ SIGNATURES = {
     "hs_prim2cons": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),
     "hs_flux": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),
     "hs_noncons_flux": (C.c_int, [_eosp, _vp, _vp, _vp, _i64, C.c_int]),
-    "hs_get_eigvals": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),
+    "hs_get_eigvals": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _vp, _i64, C.c_int]),
     "hs_hll": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "hs_lxf": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, C.c_int]),
     "hsd_problem_init": (C.c_int, [C.POINTER(HsdProblem), C.c_int, _eosp, C.c_int, _i64, _i64]),

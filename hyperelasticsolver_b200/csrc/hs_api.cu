@@ -560,7 +560,14 @@ int hs_noncons_flux(const hs_barton2009_t* eos, const double* Q, double* col, do
   return rc;
 }
 
-int hs_get_eigvals(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* eig, int64_t n, int device) {
+int hs_get_eigvals(int model, const hs_barton2009_t* eos, int nphase, const double* Q, const double* normal, double* eig,
+                   int64_t n, int device) {
+  Normal3 nrm = {{1.0, 0.0, 0.0}};
+  if (normal) {
+    const double n2 = normal[0] * normal[0] + normal[1] * normal[1] + normal[2] * normal[2];
+    if (!(fabs(n2 - 1.0) < 1e-12)) return fail(HS_ERR_ARG, "the normal must be a unit vector");
+    nrm.n[0] = normal[0]; nrm.n[1] = normal[1]; nrm.n[2] = normal[2];
+  }
   hsd_problem_t p;
   int rc = stateless_prolog(model, eos, nphase, n, device, &p); if (rc) return rc;
   DeviceGuard guard_(device);
@@ -575,9 +582,9 @@ int hs_get_eigvals(int model, const hs_barton2009_t* eos, int nphase, const doub
   const unsigned nb = (unsigned)((n * nphase + 127) / 128);
   int* st = reinterpret_cast<int*>(dst.p);
   if (model == HS_MODEL_MPH30) {
-    if (p.gen) k_eigvals<MODEL_MPH30, true><<<nb, 128>>>(din.p, dout.p, n, e, st); else k_eigvals<MODEL_MPH30, false><<<nb, 128>>>(din.p, dout.p, n, e, st);
+    if (p.gen) k_eigvals<MODEL_MPH30, true><<<nb, 128>>>(din.p, dout.p, n, e, nrm, st); else k_eigvals<MODEL_MPH30, false><<<nb, 128>>>(din.p, dout.p, n, e, nrm, st);
   } else {
-    if (p.gen) k_eigvals<MODEL_SP13, true><<<nb, 128>>>(din.p, dout.p, n, e, st); else k_eigvals<MODEL_SP13, false><<<nb, 128>>>(din.p, dout.p, n, e, st);
+    if (p.gen) k_eigvals<MODEL_SP13, true><<<nb, 128>>>(din.p, dout.p, n, e, nrm, st); else k_eigvals<MODEL_SP13, false><<<nb, 128>>>(din.p, dout.p, n, e, nrm, st);
   }
   g_launches++;
   CU(cudaGetLastError());

@@ -806,9 +806,10 @@ __global__ void __launch_bounds__(T) k_faceop(const double* __restrict__ Ql, con
 }
 
 // full get_eigvals over a Julia-layout batch (HyperelasticityMPh.jl:252-266)
+struct Normal3 { double n[3]; };
 template <int MODEL, bool GEN>
 __global__ void __launch_bounds__(128) k_eigvals(const double* __restrict__ in, double* __restrict__ eig, long long n,
-                                                 const EosPair eosp, int* status) {
+                                                 const EosPair eosp, const Normal3 nrm, int* status) {
   using MT = ModelTraits<MODEL>;
   constexpr int NPH = MT::NPH, NVAR = MT::NVAR;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -824,11 +825,12 @@ __global__ void __launch_bounds__(128) k_eigvals(const double* __restrict__ in, 
   PhaseState st;
   phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? rec[0] : 1.0, rec + 2, rec[5], rec + 6, st);
   double S6[6], ev[3];
-  phase_acoustic_sym(eos, st, S6);
+  phase_acoustic_sym_n(eos, st, nrm.n, S6);
   sym3_eigs_jacobi(S6, ev);
+  const double spd = st.u[0] * nrm.n[0] + st.u[1] * nrm.n[1] + st.u[2] * nrm.n[2];   // dot(P[3:5], n), HyperelasticityMPh.jl:264
   if (valid) {
     double* e = eig + ii * (6 * NPH) + 6 * ph;
-    for (int k = 0; k < 3; ++k) { const double ck = sqrt(fabs(ev[k])); e[k] = st.u[0] + ck; e[3 + k] = st.u[0] - ck; }
+    for (int k = 0; k < 3; ++k) { const double ck = sqrt(fabs(ev[k])); e[k] = spd + ck; e[3 + k] = spd - ck; }
   }
   int bad = __any_sync(FULL, valid ? st.bad : 0);
   if (bad && (threadIdx.x & 31) == 0) atomicOr(status, 1);

@@ -298,6 +298,36 @@ HS_HD void phase_acoustic_sym(const EosDev& eos, const PhaseState& s, double* S6
   S6[5] = cG * G[5] + cH * h33 + cg * g3 * g3;
 }
 
+// The same tensor for an arbitrary unit normal n (EquationsOfState.jl:223-246 takes n; the 1-D driver
+// only ever passes (1,0,0), main.jl:208).  With dF = e_j (x) (F^T n):  d rho = -rho n_j,
+// dG = -(g_j n^T + n g_j^T), so the closed form above holds with e_1 -> n, g1 -> G n, h1 -> G^2 n,
+// G11 -> n.G n.  Needs the full state (not on the hot path: used by hs_get_eigvals only).
+HS_HD void phase_acoustic_sym_n(const EosDev& eos, const PhaseState& s, const double* n, double* S6) {
+  const double* G = s.G;
+  const double Gm[3][3] = {{G[0], G[1], G[2]}, {G[1], G[3], G[4]}, {G[2], G[4], G[5]}};
+  double H[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) H[i][j] = Gm[i][0] * Gm[0][j] + Gm[i][1] * Gm[1][j] + Gm[i][2] * Gm[2][j];
+  double gn[3], hn[3];
+  for (int i = 0; i < 3; ++i) {
+    gn[i] = Gm[i][0] * n[0] + Gm[i][1] * n[1] + Gm[i][2] * n[2];
+    hn[i] = H[i][0] * n[0] + H[i][1] * n[1] + H[i][2] * n[2];
+  }
+  const double nGn = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
+  const double e1 = s.a - s.e2 * s.I1;
+  const double cG = -2.0 * (s.e2 * nGn - s.a), cH = -2.0 * s.e2, cg = cH * (1.0 / 3.0);
+  const double kg = -2.0 * (0.5 * eos.hbeta * e1 - s.a * (1.0 + eos.hbeta));
+  const double kh = cH * (1.0 + eos.eb);
+  const double dE3c = eos.kA1 * eos.ha * s.uc2 + eos.hg * eos.hg * s.th + eos.hb * eos.hbeta * eos.hbeta * s.rB * s.J;
+  const double k11 = 2.0 * (2.0 * dE3c + s.E3);
+  const int ix[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+  for (int k = 0; k < 6; ++k) {
+    const int i = ix[k][0], j = ix[k][1];
+    S6[k] = cG * Gm[i][j] + cH * H[i][j] + cg * gn[i] * gn[j] + kg * (gn[i] * n[j] + n[i] * gn[j]) +
+            kh * (hn[i] * n[j] + n[i] * hn[j]) + k11 * n[i] * n[j];
+  }
+}
+
 // c_max = sqrt(max_k |eig_k(Omega)|): the only thing any consumer of get_eigvals keeps
 // (main.jl:210, NumFluxes.jl:90-91 take min / max / max|.| of u1 +- c_k).
 HS_HD double phase_cmax(const EosDev& eos, const PhaseState& s) {

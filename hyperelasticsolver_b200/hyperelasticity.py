@@ -40,10 +40,11 @@ def flux(eos, Q, device=0):
     return _op(L.lib().hs_flux, eos, Q, device)
 
 
-def get_eigvals(eos, Q, device=0):
+def get_eigvals(eos, Q, n=(1, 0, 0), device=0):
     a = np.ascontiguousarray(Q, dtype=np.float64)
+    nn = np.ascontiguousarray(n, dtype=np.float64)
     eig = np.empty(a.shape[:-1] + (6,))
-    L.check(L.lib().hs_get_eigvals(_MODEL, L.eos_array(eos, _MODEL), 1, a.ctypes.data, eig.ctypes.data, a.size // 13, device))
+    L.check(L.lib().hs_get_eigvals(_MODEL, L.eos_array(eos, _MODEL), 1, a.ctypes.data, nn.ctypes.data, eig.ctypes.data, a.size // 13, device))
     return eig
 
 

@@ -64,13 +64,14 @@ def noncons_flux(eos, Q, dense=True, device=0):
 
 
 def get_eigvals(eos, Q, n=(1, 0, 0), device=0):
-    """HyperelasticityMPh.jl:252-266: per phase [u.n + c_k, u.n - c_k], k = 1..3.  Only the
-    x-normal of the 1-D solver (main.jl:208) is implemented."""
-    if tuple(float(v) for v in n) != (1.0, 0.0, 0.0):
-        raise NotImplementedError("only n = [1, 0, 0] (the reference's 1-D driver, main.jl:208)")
+    """HyperelasticityMPh.jl:252-266: per phase [u.n + c_k, u.n - c_k], k = 1..3, for a unit normal `n`
+    (the reference's 1-D driver passes [1, 0, 0], main.jl:208)."""
+    nn = np.ascontiguousarray(n, dtype=np.float64)
+    if nn.shape != (3,):
+        raise ValueError("n must have 3 components")
     a, shp, cnt = _batch(Q, 30)
     eig = np.empty(shp[:-1] + (12,))
-    L.check(L.lib().hs_get_eigvals(_MODEL, L.eos_array(eos, _MODEL), 2, a.ctypes.data, eig.ctypes.data, cnt, device))
+    L.check(L.lib().hs_get_eigvals(_MODEL, L.eos_array(eos, _MODEL), 2, a.ctypes.data, nn.ctypes.data, eig.ctypes.data, cnt, device))
     return eig
 
 

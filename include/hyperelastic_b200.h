@@ -100,8 +100,10 @@ int hs_flux(int model, const hs_barton2009_t* eos, int nphase, const double* Q, 
 /* noncons_flux HyperelasticityMPh.jl:178-250.  col (30, n): column 1 of each 15x15 diagonal
  * block (the only non-zero entries, :223-230).  Bdense (30, 30, n) gets the full matrix if not NULL. */
 int hs_noncons_flux(const hs_barton2009_t* eos, const double* Q, double* col, double* Bdense, int64_t n, int device);
-/* get_eigvals HyperelasticityMPh.jl:252-266 with n = (1,0,0): eig (6*nphase, n) */
-int hs_get_eigvals(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* eig, int64_t n, int device);
+/* get_eigvals HyperelasticityMPh.jl:252-266: eig (6*nphase, n), per phase [u.n + c_k, u.n - c_k].
+ * normal: unit vector (3 doubles) or NULL for (1,0,0), the only normal the 1-D driver uses (main.jl:208). */
+int hs_get_eigvals(int model, const hs_barton2009_t* eos, int nphase, const double* Q, const double* normal, double* eig,
+                   int64_t n, int device);
 /* hll NumFluxes.jl:70-132: Ql, Qr (30, n); eig_l, eig_r (12, n) = get_eigvals of the two cells
  * (the `eigvals` argument, main.jl:56-57).  cons = zeros (NumFluxes.jl:82), dm = D^-, dp = D^+,
  * s (2, n) = [s_l, s_r] (may be NULL).  For SP13 (nvar 13, eig 6 x n) cons is the conservative

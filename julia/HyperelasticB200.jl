@@ -66,10 +66,10 @@ function noncons_flux(eos::Tuple{Barton2009,Barton2009}, Q::Vector{Float64}; dev
 end
 
 function get_eigvals(eos::Tuple{Barton2009,Barton2009}, Q::VecOrMat{Float64}, n::Array{<:Any,1}; device::Integer=0)
-  n == [1, 0, 0] || error("only n = [1,0,0] (main.jl:208)")
+  nn = Vector{Float64}(n)   # unit normal; main.jl:208 passes [1, 0, 0]
   E = Q isa AbstractVector ? zeros(12) : zeros(12, size(Q, 2)); e = eosvec(eos)
-  GC.@preserve Q E e check(ccall((:hs_get_eigvals, LIB), Cint,
-      (Cint, Ptr{Barton2009}, Cint, Ptr{Float64}, Ptr{Float64}, Int64, Cint), HS_MODEL_MPH30, e, 2, Q, E, ncols(Q), device))
+  GC.@preserve Q E e nn check(ccall((:hs_get_eigvals, LIB), Cint,
+      (Cint, Ptr{Barton2009}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Cint), HS_MODEL_MPH30, e, 2, Q, nn, E, ncols(Q), device))
   return E
 end
 

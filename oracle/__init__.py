@@ -48,6 +48,7 @@ def lib():
         L.hso_flux.argtypes = [_dp, C.c_int, _dp, _dp, i64]
         L.hso_noncons_flux.argtypes = [_dp, _dp, _dp, _dp, i64]
         L.hso_get_eigvals.argtypes = [_dp, C.c_int, _dp, _dp, i64]
+        L.hso_get_eigvals_n.argtypes = [_dp, _dp, _dp, _dp, i64]
         L.hso_energy.argtypes = [_dp, C.c_double, _dp]; L.hso_energy.restype = C.c_double
         L.hso_entropy.argtypes = [_dp, C.c_double, _dp]; L.hso_entropy.restype = C.c_double
         L.hso_temperature.argtypes = [_dp, C.c_double, _dp]; L.hso_temperature.restype = C.c_double
@@ -126,6 +127,14 @@ def get_eigvals(eos, model, Q):
     Q = _f(Q); n = Q.size // NVAR[model]
     eig = np.empty((n, NEIG[model]))
     st = lib().hso_get_eigvals(_p(eos_block(eos)), model, _p(Q), _p(eig), n)
+    return eig, st
+
+
+def get_eigvals_n(eos, Q, n):
+    """two-phase get_eigvals for an arbitrary normal n"""
+    Q = _f(Q); cnt = Q.size // 30
+    eig = np.empty((cnt, 12))
+    st = lib().hso_get_eigvals_n(_p(eos_block(eos)), _p(Q), _p(_f(n)), _p(eig), cnt)
     return eig, st
 
 

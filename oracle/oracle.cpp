@@ -658,6 +658,14 @@ int hso_get_eigvals(const double* eos, int model, const double* Q, double* eig, 
   return g_domain_error;
 }
 
+// get_eigvals for an arbitrary normal n (two-phase), HyperelasticityMPh.jl:252-266
+int hso_get_eigvals_n(const double* eos, const double* Q, const double* n, double* eig, int64_t cnt) {
+  const Eos* e = reinterpret_cast<const Eos*>(eos);
+  g_domain_error = 0;
+  for (int64_t i = 0; i < cnt; ++i) get_eigvals(e, 2, Q + 30 * i, n, eig + 12 * i);
+  return g_domain_error;
+}
+
 // individual EoS entry points (double), for unit tests
 double hso_energy(const double* eos, double S, const double* G) { return energy(*reinterpret_cast<const Eos*>(eos), S, G); }
 double hso_entropy(const double* eos, double e_int, const double* G) { return entropy(*reinterpret_cast<const Eos*>(eos), e_int, G); }

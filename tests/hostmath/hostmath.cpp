@@ -19,6 +19,13 @@ void hm_phase(const double* eos_abi, int gen, double alpha, const double* m, dou
   phase_acoustic_sym(e, s, out + k); k += 6;
   out[k++] = s.bad;
 }
+// symmetrised acoustic tensor for a general unit normal
+void hm_acoustic_n(const double* eos_abi, int gen, double alpha, const double* m, double E, const double* A, const double* n, double* S6) {
+  EosDev e = make_eos_dev(*reinterpret_cast<const EosAbi*>(eos_abi));
+  PhaseState s;
+  if (gen) phase_state<true>(e, alpha, m, E, A, s); else phase_state<false>(e, alpha, m, E, A, s);
+  phase_acoustic_sym_n(e, s, n, S6);
+}
 void hm_sym3_eigs(const double* a, double* ev) { sym3_eigs(a, ev); }
 void hm_sym3_eigs_jacobi(const double* a, double* ev) { sym3_eigs_jacobi(a, ev); }
 double hm_sym3_max_abs(const double* a) { return sym3_max_abs_eig(a); }

@@ -278,3 +278,34 @@ def test_config4_ensemble_sample_of_64(gpu, oracle, model):
     nv = Q0.shape[-1]
     assert relerr(sol.local().reshape(-1, nv), ref["Q"].reshape(-1, nv)) < 1e-9
     assert np.allclose(sol.t, ref["t"], rtol=1e-11) and len(set(np.round(sol.t, 12))) > 32    # genuinely different dt per problem
+
+
+def test_get_eigvals_general_normal_and_full_sweep(gpu, oracle):
+    """SURVEY 8(f3): the physics takes a normal n (EquationsOfState.jl:223, HyperelasticityMPh.jl:264);
+    plus the full-spectrum CFL sweep of a resident grid (hs_wave_speeds with eig != NULL)."""
+    hs = gpu
+    rng = np.random.default_rng(21)
+    eos = (hs.Barton2009(), hs.Barton2009()); oe = [oracle.barton2009()] * 2
+    Q = hs.prim2cons_mph(eos, random_mph_prims(rng, 40))
+    for n in ([0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.6, 0.0, 0.8], list(np.array([1.0, -2.0, 0.5]) / np.linalg.norm([1.0, -2.0, 0.5]))):
+        eg = hs.get_eigvals(eos, Q, n)
+        ego, st = oracle.get_eigvals_n(oe, Q, n)
+        assert st == 0 and relerr(eg, ego, per_var=False) < 1e-12
+    with pytest.raises(hs.HyperelasticError):
+        hs.get_eigvals(eos, Q, [2.0, 0.0, 0.0])          # not a unit vector
+    # anchor: F = I, S = 0 -> speeds (b0, b0, c0) for any direction (isotropy of the reference state)
+    P = np.zeros(30)
+    for p in range(2):
+        P[15 * p:15 * p + 15] = [0.5, 8.93, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1]
+    e0 = hs.get_eigvals(eos, hs.prim2cons_mph(eos, P), [0.0, 0.6, 0.8])
+    assert np.allclose(e0[:3], [2.1, 2.1, 4.6], rtol=1e-12) and np.allclose(e0[3:6], [-2.1, -2.1, -4.6], rtol=1e-12)
+    # full sweep on a resident grid
+    nx = 77
+    Ql, Qr = hs.initial_states(eos, 7)
+    Q0 = hs.initial_condition(Ql, Qr, nx)
+    with hs.Solver(eos, nx) as sol:
+        sol.upload(Q0); sol.step()
+        lam, eig = sol.wave_speeds(full=True)
+        Q1 = sol.download()
+    ego, _ = oracle.get_eigvals(oe, oracle.MPH30, Q1)
+    assert relerr(eig, ego, per_var=False) < 1e-12 and abs(lam[0] - np.abs(ego).max()) < 1e-12 * lam[0]

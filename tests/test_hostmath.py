@@ -91,3 +91,26 @@ def test_sym3_eigs(hm):
     hm.hm_sym3_eigs_jacobi(_p(a), _p(ev))
     assert np.array_equal(ev, [3.0, 3.0, 3.0])
     assert hm.hm_sym3_max_abs(_p(a)) == 3.0
+
+
+def test_acoustic_general_normal(hm, oracle):
+    """closed form for an arbitrary unit normal (hs_get_eigvals) vs the nested-dual jacobian"""
+    dp = C.POINTER(C.c_double)
+    hm.hm_acoustic_n.argtypes = [dp, C.c_int, C.c_double, dp, C.c_double, dp, dp, dp]
+    rng = np.random.default_rng(2)
+    for eos, gen in ((oracle.barton2009(), 0), (oracle.barton2009(c0=6.22, cv=9e-4, b0=3.16, beta=3.577, gamma=2.088), 1)):
+        for it in range(60):
+            alpha = rng.uniform(0.1, 0.9); F = np.eye(3) + 0.1 * rng.uniform(-1, 1, (3, 3))
+            u = rng.uniform(-1, 1, 3); S = rng.uniform(0, 1e-3)
+            n = rng.normal(size=3); n /= np.linalg.norm(n)
+            if it % 5 == 0:
+                n = np.array([0.0, 1.0, 0.0])
+            Pp = np.array([alpha, 8.9 / np.linalg.det(F), *u, S, *F.flatten(order="F")])
+            Q, _ = oracle.prim2cons([eos, eos], 1, np.concatenate([Pp, Pp]))
+            Po, _ = oracle.cons2prim([eos, eos], 1, Q)
+            ac = oracle.acoustic(eos, Po[5], Po[6:15], n)
+            S6 = np.zeros(6); m = np.ascontiguousarray(Q[2:5]); A = np.ascontiguousarray(Q[6:15]); nn = np.ascontiguousarray(n)
+            hm.hm_acoustic_n(_p(eos), gen, Q[0], _p(m), Q[5], _p(A), _p(nn), _p(S6))
+            ref = 0.5 * (ac + ac.T)
+            r6 = np.array([ref[0, 0], ref[0, 1], ref[0, 2], ref[1, 1], ref[1, 2], ref[2, 2]])
+            assert np.abs(S6 - r6).max() < 1e-12 * np.abs(r6).max()
