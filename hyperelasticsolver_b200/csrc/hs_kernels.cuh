@@ -147,23 +147,27 @@ __device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const d
   }
 }
 
-// acc[j] += dalpha * sum_q w_q c_j(psi(s_q)),  psi(s) = a (1-s) + b s        (NumFluxes.jl:97-107)
-// a, b: shared-memory columns (row stride T) of this thread's phase.  MPh only.
-template <bool GEN, int T>
-__device__ __forceinline__ void path_integral(const EosDev& eos, const double* a, const double* b, const double* xs,
+// acc[j] += dalpha * sum_q w_q c_j(psi(s_q)) along the straight path between two records
+// (NumFluxes.jl:97-107).  The path is given as a base column and a DELTA column d = end - start
+// (shared memory, row stride T; d[0] = dalpha):
+//   FROM_END = false: psi(s) = base + s d          (base = start of the segment)
+//   FROM_END = true : psi(s) = base - (1 - s) d    (base = end of the segment)
+// i.e. one fused multiply-add per component instead of the two of Q_l (1-s) + Q_r s.  MPh only.
+template <bool GEN, int T, bool FROM_END>
+__device__ __forceinline__ void path_integral(const EosDev& eos, const double* base, const double* d, const double* xs,
                                               const double* ws, double* acc, int& bad) {
-  const double dalpha = b[0] - a[0];
+  const double dalpha = d[0];
   constexpr int NODE_UNROLL = HS_NODE_UNROLL;
 #pragma unroll NODE_UNROLL
   for (int q = 0; q < 6; ++q) {
-    const double s = xs[q], oms = 1.0 - s, w = ws[q] * dalpha;
-    const double alpha = a[0] * oms + b[0] * s;
+    const double s = FROM_END ? xs[q] - 1.0 : xs[q], w = ws[q] * dalpha;
+    const double alpha = fma(s, dalpha, base[0]);
     double m[3], A[9];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) m[k] = a[(2 + k) * T] * oms + b[(2 + k) * T] * s;
-    const double E = a[5 * T] * oms + b[5 * T] * s;
+    for (int k = 0; k < 3; ++k) m[k] = fma(s, d[(2 + k) * T], base[(2 + k) * T]);
+    const double E = fma(s, d[5 * T], base[5 * T]);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) A[k] = a[(6 + k) * T] * oms + b[(6 + k) * T] * s;
+    for (int k = 0; k < 9; ++k) A[k] = fma(s, d[(6 + k) * T], base[(6 + k) * T]);
     PhaseState st;
     phase_state<GEN>(eos, alpha, m, E, A, st);
     bad |= st.bad;
@@ -210,16 +214,24 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
       double acc[15];
 #pragma unroll
       for (int j = 0; j < 15; ++j) acc[j] = 0.0;
-      path_integral<GEN, T>(eos, a, b, c_gleg_x, c_gleg_w, acc, bad);                 // B_int(Q_l, Q_r)
+      // H (this thread's private column) holds the delta of the segment being integrated
+#pragma unroll
+      for (int j = 0; j < 15; ++j)
+        if (j != 1) H[j * T] = b[j * T] - a[j * T];      // alpha*rho (slot 1) is never read by the physics
+      path_integral<GEN, T, false>(eos, a, H, c_gleg_x, c_gleg_w, acc, bad);           // B_int(Q_l, Q_r)
 #pragma unroll
       for (int j = 0; j < 15; ++j) {
-        if (j == 1) continue;  // alpha*rho is never read by the physics
+        if (j == 1) continue;
         const double path = (acc[j] + Fb[j * T]) - Fa[j * T];                         // :109
-        H[j * T] = ((b[j * T] * s_r - a[j * T] * s_l) - path) * inv_ds;               // :111  Q_hll
+        const double qh = ((b[j * T] * s_r - a[j * T] * s_l) - path) * inv_ds;        // :111  Q_hll
+        H[j * T] = qh - a[j * T];
         acc[j] = 0.0;
       }
-      path_integral<GEN, T>(eos, a, H, c_gleg_x, c_gleg_w, acc, bad);                 // B_int(Q_l, Q_hll)
-      path_integral<GEN, T>(eos, H, b, c_gleg_x, c_gleg_w, acc, bad);                 // B_int(Q_hll, Q_r)
+      path_integral<GEN, T, false>(eos, a, H, c_gleg_x, c_gleg_w, acc, bad);           // B_int(Q_l, Q_hll)
+#pragma unroll
+      for (int j = 0; j < 15; ++j)
+        if (j != 1) H[j * T] = (b[j * T] - a[j * T]) - H[j * T];                      // Q_r - Q_hll
+      path_integral<GEN, T, true>(eos, b, H, c_gleg_x, c_gleg_w, acc, bad);            // B_int(Q_hll, Q_r)
       const double k_m = -s_l * inv_ds, k_p = s_r * inv_ds;
 #pragma unroll
       for (int j = 0; j < 15; ++j) {                                                   // :128-129
@@ -236,7 +248,12 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
     double acc[15];
 #pragma unroll
     for (int j = 0; j < 15; ++j) acc[j] = 0.0;
-    if (MPH) path_integral<GEN, T>(eos, a, b, c_glob_x, c_glob_w, acc, bad);           // NumFluxes.jl:35-47
+    if (MPH) {                                                                         // NumFluxes.jl:35-47
+#pragma unroll
+      for (int j = 0; j < 15; ++j)
+        if (j != 1) H[j * T] = b[j * T] - a[j * T];
+      path_integral<GEN, T, false>(eos, a, H, c_glob_x, c_glob_w, acc, bad);
+    }
 #pragma unroll
     for (int j = J0; j < 15; ++j) {
       const double cons = 0.5 * (Fa[j * T] + Fb[j * T]) - 0.5 * lambda * (b[j * T] - a[j * T]);  // :30
