@@ -1,8 +1,9 @@
 #!/bin/bash
-# development aid: bench.py at N = 1,2,4,8 on one box (the driver runs the same sweep at round end)
+# development aid: bench.py at several GPU counts on one box (the driver runs the same sweep at round end)
+#   tools/scale_sweep.sh WORKLOAD STEPS "1 2 4 8"
 mkdir -p gpurun_out
-W=${1:-sp13_2p24}; STEPS=${2:-20}
-for n in 1 2 4 8; do
+W=${1:-sp13_2p24}; STEPS=${2:-20}; NS=${3:-"1 2 4 8"}
+for n in $NS; do
   if [ $n -eq 1 ]; then
     python bench.py --workload $W --steps $STEPS --no-cpu-baseline > gpurun_out/scale_${W}_$n.log 2>&1
   else
@@ -12,7 +13,7 @@ for n in 1 2 4 8; do
 import sys, json
 l = sys.stdin.readline()
 try:
-    d = json.loads(l); print(d['n_gpus'], 'value %.4e' % d['value'], 'ms/step %.3f' % d['ms_per_step'], 'kernel_ms %.3f' % d['roofline']['kernel_ms'], 'e2e %.3e' % d['e2e']['value'], d['clocks'])
+    d = json.loads(l); print(d['n_gpus'], 'value %.4e' % d['value'], 'ms/step %.4f' % d['ms_per_step'], 'kernel_ms %.4f' % d['roofline']['kernel_ms'], 'e2e %.3e' % d['e2e']['value'], d['config']['parallelism'][:60], d['clocks'])
 except Exception as e:
     print('FAILED', l[:300])
 "
