@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -291,15 +291,17 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     alg_bytes = 2 * nvar * 8 * updated_local
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, fp64_pct = None, None
     tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp):   # per-launch DRAM bytes / FP64-pipe utilisation of the same kernel from the committed ncu capture
         tj = json.load(open(tp)).get(args.workload)
-        if tj:
+        if tj and world == 1:
             traffic = tj.get("dram_bytes_per_launch")
+            fp64_pct = tj.get("fp64_pipe_pct_of_peak")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k_step (fused flux + update + next-step wave bounds)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_cell_update": 2 * nvar * 8, "cell_updates_per_launch": updated_local, "peak_source": peak_src,
+                "fp64_pipe_pct_ncu": fp64_pct, "fp64_issue_peak_dfma_per_s": 1.708e13,
                 "note": "the path is FP64-pipe bound, not HBM bound (DESIGN.md): see profiles/ for the measured DFMA peak and pipe utilisation"}
 
     # ---- end to end through the host-buffer API ------------------------------------------------
