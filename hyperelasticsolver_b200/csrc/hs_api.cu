@@ -332,7 +332,6 @@ int hs_download(hs_ctx_t* c, double* Q) {
 
 int hs_set_time(hs_ctx_t* c, double t, int64_t step) {
   CTX_ENTER(c);
-  int rc = HS_OK;
   const int64_t np = c->prob.nprob;
   std::vector<double> tv(np, t);
   std::vector<long long> sv(np, step);

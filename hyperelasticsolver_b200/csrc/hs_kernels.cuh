@@ -318,7 +318,6 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
   // cached bounds) before anything consumes them, so their latencies overlap.
   const unsigned long long lam_bits = __ldg(g.lam + (size_t)g.cur * g.nprob + prob);
   const double t_cur = __ldg(g.tt + (size_t)g.cur * g.nprob + prob);
-  constexpr int NAUX = MT::NAUX;
   double rin[15], lo_in_r = 0.0, hi_in_r = 0.0, ax[MODEL == MODEL_SP13 ? 4 : 1];
   if (MODEL == MODEL_MPH30) {
 #pragma unroll
