@@ -57,6 +57,12 @@ __constant__ double c_glob_w[6] = {0.06666666666666666667 / 2.0, 0.3784749562978
 // 6-14 A = alpha*rho*F column-major.  SP13 variable v lives in slot sp_slot(v); slots 0,1 unused.
 __host__ __device__ constexpr int sp_slot(int v) { return v < 3 ? 2 + v : (v == 12 ? 5 : 6 + ((v - 3) / 3) + 3 * ((v - 3) % 3)); }
 
+// Physical-flux slots that are identically zero (alpha, and the A_1j row: u1 A_1j - u1 A_1j) are not
+// stored: the shared flux tile has 11 rows (slots 1..5, 7, 8, 10, 11, 13, 14).
+__host__ __device__ constexpr bool flux_is_zero(int j) { return j == 0 || j == 6 || j == 9 || j == 12; }
+__host__ __device__ constexpr int flux_row(int j) { return j - 1 - (j > 6) - (j > 9) - (j > 12); }
+#define HS_FLUX(F, j) (flux_is_zero(j) ? 0.0 : (F)[flux_row(j) * T])
+
 template <int MODEL> struct ModelTraits;
 // NAUX: cached per-cell rows next to the state.  Rows 0,1 = wave bounds lo / hi (all any consumer of
 // get_eigvals keeps).  The single-phase model also caches 1/rho and row 1 of the stress (rows 2..5):
@@ -222,7 +228,7 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
 #pragma unroll
       for (int j = 0; j < 15; ++j) {
         if (j == 1) continue;
-        const double path = (acc[j] + Fb[j * T]) - Fa[j * T];                         // :109
+        const double path = (acc[j] + HS_FLUX(Fb, j)) - HS_FLUX(Fa, j);                         // :109
         const double qh = ((b[j * T] * s_r - a[j * T] * s_l) - path) * inv_ds;        // :111  Q_hll
         H[j * T] = qh - a[j * T];
         acc[j] = 0.0;
@@ -235,14 +241,14 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
       const double k_m = -s_l * inv_ds, k_p = s_r * inv_ds;
 #pragma unroll
       for (int j = 0; j < 15; ++j) {                                                   // :128-129
-        const double br = (Fb[j * T] - Fa[j * T]) + (j == 1 ? 0.0 : acc[j]);
+        const double br = (HS_FLUX(Fb, j) - HS_FLUX(Fa, j)) + (j == 1 ? 0.0 : acc[j]);
         const double dq = k_q * (b[j * T] - a[j * T]);
         emit(j, 0.0, k_m * br + dq, k_p * br - dq);
       }
     } else {
 #pragma unroll
       for (int j = J0; j < 15; ++j)                                                    // NumFluxes.jl:78 (one-phase form)
-        emit(j, (s_r * Fa[j * T] - s_l * Fb[j * T]) * inv_ds + k_q * (b[j * T] - a[j * T]), 0.0, 0.0);
+        emit(j, (s_r * HS_FLUX(Fa, j) - s_l * HS_FLUX(Fb, j)) * inv_ds + k_q * (b[j * T] - a[j * T]), 0.0, 0.0);
     }
   } else {
     double acc[15];
@@ -256,7 +262,7 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
     }
 #pragma unroll
     for (int j = J0; j < 15; ++j) {
-      const double cons = 0.5 * (Fa[j * T] + Fb[j * T]) - 0.5 * lambda * (b[j * T] - a[j * T]);  // :30
+      const double cons = 0.5 * (HS_FLUX(Fa, j) + HS_FLUX(Fb, j)) - 0.5 * lambda * (b[j * T] - a[j * T]);  // :30
       const double d = (MPH && j != 1) ? 0.5 * acc[j] : 0.0;                                       // :50-51
       emit(j, cons, d, d);
     }
@@ -280,9 +286,9 @@ struct StepArgs {
   EosPair eos;
 };
 
-// rows J0..14 of the three tile arrays + cached bounds + reduction scratch
+// rows J0..14 of the record and scratch tiles, the non-zero flux rows, cached bounds, reduction scratch
 template <int MODEL, int T> constexpr size_t step_smem_bytes() {
-  return sizeof(double) * (3 * (15 - ModelTraits<MODEL>::J0) * T + 2 * T + 32);
+  return sizeof(double) * ((2 * (15 - ModelTraits<MODEL>::J0) + 11 - flux_row(ModelTraits<MODEL>::J0 < 1 ? 1 : ModelTraits<MODEL>::J0)) * T + 2 * T + 32);
 }
 
 // resident blocks per SM the register allocation is capped for (tuned on B200, profiles/)
@@ -300,10 +306,11 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
   // Three tile arrays of NROW = 15 - J0 rows (the single-phase model has no slots 0,1); the
   // pointers are biased by -J0 rows so that slot j is always row j.
   constexpr int NROW = 15 - J0;
-  double* Rs = smem - J0 * T;          // records        [J0..14][T]
-  double* Fs = Rs + NROW * T;          // physical flux  [J0..14][T]
-  double* Hs = Fs + NROW * T;          // Q_hll, then the fluctuation handed to the left cell
-  double* lo_s = smem + 3 * NROW * T;  // [CPB]
+  constexpr int F0 = flux_row(J0 < 1 ? 1 : J0), NFROW = 11 - F0;   // first stored flux row, number of flux rows
+  double* Rs = smem - J0 * T;                  // records        [J0..14][T]
+  double* Hs = smem + NROW * T - J0 * T;       // Q_hll / path deltas, then the fluctuation handed to the left cell
+  double* Fs = smem + 2 * NROW * T - F0 * T;   // physical flux, non-zero slots only (flux_row)
+  double* lo_s = smem + (2 * NROW + NFROW) * T;  // [CPB]
   double* hi_s = lo_s + T;      // [CPB]
   double* red = hi_s + T;       // [T/32]
 
@@ -378,7 +385,8 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     double f[15];
     sp_flux_cached(rin, ax[0], ax + 1, f);   // state recovery was done by the previous step's CFL sweep
 #pragma unroll
-    for (int j = J0; j < 15; ++j) Fs[j * T + tid] = f[j];
+    for (int j = J0; j < 15; ++j)
+      if (!flux_is_zero(j)) Fs[flux_row(j) * T + tid] = f[j];
   } else {
     PhaseState st;
     column_state<MODEL, GEN, T>(eos, Rs + tid, st);
@@ -388,7 +396,8 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     for (int k = 0; k < 9; ++k) A[k] = Rs[(6 + k) * T + tid];
     phase_flux(st, A, f);
 #pragma unroll
-    for (int j = J0; j < 15; ++j) Fs[j * T + tid] = f[j];
+    for (int j = J0; j < 15; ++j)
+      if (!flux_is_zero(j)) Fs[flux_row(j) * T + tid] = f[j];
   }
   __syncthreads();
 
@@ -796,7 +805,8 @@ __global__ void __launch_bounds__(T) k_faceop(const double* __restrict__ Ql, con
     double A[9], f[15];
     for (int k = 0; k < 9; ++k) A[k] = R[(6 + k) * T];
     phase_flux(st, A, f);
-    for (int j = 0; j < 15; ++j) F[j * T] = f[j];
+    for (int j = 1; j < 15; ++j)
+      if (!flux_is_zero(j)) F[flux_row(j) * T] = f[j];
   }
   double lo_l = 0.0, hi_r = 0.0;
   if (FLUX == FLUX_HLL) {
