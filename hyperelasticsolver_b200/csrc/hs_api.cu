@@ -42,6 +42,12 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+struct DevBufRaw {   // scoped device allocation on the current device
+  double* p = nullptr;
+  ~DevBufRaw() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n * sizeof(double)); }
+};
+
 static_assert(sizeof(EosDev) <= sizeof(double) * 20, "EosDev must fit hsd_problem_t::eos_dev");
 static_assert(sizeof(hs_barton2009_t) == sizeof(EosAbi), "ABI struct mismatch");
 
@@ -234,174 +240,294 @@ double* hsd_scal_steps(double* scal, int64_t nprob) { return scal + 6 * nprob; }
 double* hsd_scal_status(double* scal, int64_t nprob) { return scal + HS_SCAL_SLOTS * nprob; }
 
 // ---------------------------------------------------------------------------------------------
-// stateful context (host-buffer ABI)
+// stateful context (host-buffer ABI).  One context = one grid (or ensemble) on one device, or one
+// grid slab-decomposed over several devices of this process (hs_create_multi): the drop-in for a
+// single-process driver such as `julia main.jl`.  With several devices every step is one fused
+// kernel per device followed by one k_exchange_p2p per device (peer access, no NCCL).
 // ---------------------------------------------------------------------------------------------
+namespace {
+struct Part {                 // one slab on one device
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  hsd_problem_t prob;         // ncells = local cells (halo cells included)
+  int64_t a = 0, b = 0;       // owned global cells [a, b)
+  int64_t lo_g = 0;           // global index of local cell 0
+  int ghost = 0;
+  double* Q[2] = {nullptr, nullptr};
+  double* aux[2] = {nullptr, nullptr};
+  double* scal = nullptr;
+  double* stage = nullptr;    // AoS staging, nvar * local cells
+  double* mbox = nullptr;     // exchange mailbox (multi-device only)
+};
+}  // namespace
+
 struct hs_ctx {
-  hsd_problem_t prob;
-  int device;
-  int nvar;
-  cudaStream_t stream;
-  double* Q[2];
-  double* aux[2];     // [NAUX][stride] cached per-cell rows (wave bounds, ...)
-  double* scal;
-  double* stage;      // AoS staging, nvar*stride doubles
-  double* dt_hist;    // device, grown on demand
-  int64_t hist_cap;
-  int64_t n;          // launch counter since the last upload (selects buffers and scalar slots)
+  int model = 0, nvar = 0, nphase = 0;
+  int64_t ncells = 0, nprob = 0;
+  std::vector<Part> parts;
+  std::vector<void*> mailboxes;
+  double* dt_hist = nullptr;  // on parts[0].device, grown on demand
+  int64_t hist_cap = 0;
+  int64_t n = 0;              // launch counter since the last upload (selects buffers and scalar slots)
+  uint64_t xseq = 0;          // exchange sequence number (never reused)
 };
 
-#define CTX_ENTER(c)                                             \
-  if (!(c)) return fail(HS_ERR_ARG, "null context");               \
-  DeviceGuard guard_((c)->device);                                 \
+#define PART_ENTER(p)                                              \
+  DeviceGuard guard_((p).device);                                  \
   if (!guard_.ok) return fail(HS_ERR_CUDA, "cudaSetDevice failed")
 
-int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob, int device) {
+static int create_impl(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob,
+                       const int* devices, int ndev) {
   if (!out) return fail(HS_ERR_ARG, "null ctx pointer");
   *out = nullptr;
   if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  if (ndev < 1 || ndev > MBOX_MAXR || !devices) return fail(HS_ERR_ARG, "1..8 devices");
+  if (ndev > 1 && nprob != 1) return fail(HS_ERR_ARG, "several devices: one slab-decomposed grid (nprob == 1)");
+  hsd_problem_t whole;
+  int rc = hsd_problem_init(&whole, model, eos, nphase, ncells, nprob);
+  if (rc) return rc;
+  if (ndev > 1 && ncells / ndev < 3) return fail(HS_ERR_ARG, "slabs too small: need >= 3 cells per device");
   hs_ctx* c = new hs_ctx();
-  std::memset(c, 0, sizeof *c);
-  int rc = hsd_problem_init(&c->prob, model, eos, nphase, ncells, nprob);
-  if (rc) { delete c; return rc; }
-  c->device = device;
-  c->nvar = model == HS_MODEL_MPH30 ? 30 : 13;
+  c->model = model; c->nvar = model == HS_MODEL_MPH30 ? 30 : 13; c->nphase = nphase; c->ncells = ncells; c->nprob = nprob;
+  c->parts.resize(ndev);
   auto bail = [&](int code) { hs_destroy(c); return code; };
-  DeviceGuard guard_(device);
-  if (!guard_.ok) { delete c; return fail(HS_ERR_CUDA, "cudaSetDevice failed"); }
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(HS_ERR_CUDA, "stream creation failed"); }
-  const size_t nq = (size_t)c->nvar * c->prob.stride * sizeof(double), nb = (size_t)HS_NAUX(model) * c->prob.stride * sizeof(double);
-  cudaError_t e = cudaSuccess;
-  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-    e = cudaMalloc(&c->Q[k], nq);
-    if (e == cudaSuccess) e = cudaMalloc(&c->aux[k], nb);
+  for (int r = 0; r < ndev; ++r) {
+    Part& p = c->parts[r];
+    p.device = devices[r];
+    p.a = ncells * r / ndev; p.b = ncells * (r + 1) / ndev;                  // same partition as slab.py::slab_bounds
+    p.lo_g = p.a - (r > 0 ? 1 : 0);
+    const int64_t hi_g = p.b + (r < ndev - 1 ? 1 : 0);
+    p.ghost = (r > 0 ? 1 : 0) | (r < ndev - 1 ? 2 : 0);
+    rc = hsd_problem_init(&p.prob, model, eos, nphase, hi_g - p.lo_g, nprob);
+    if (rc) return bail(rc);
+    DeviceGuard g(p.device);
+    if (!g.ok) return bail(fail(HS_ERR_CUDA, "cudaSetDevice failed"));
+    cudaError_t e = cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking);
+    const size_t nq = (size_t)c->nvar * p.prob.stride * sizeof(double), nb = (size_t)HS_NAUX(model) * p.prob.stride * sizeof(double);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+      e = cudaMalloc(&p.Q[k], nq);
+      if (e == cudaSuccess) e = cudaMalloc(&p.aux[k], nb);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&p.scal, sizeof(double) * HS_SCAL_DOUBLES(nprob));
+    if (e == cudaSuccess) e = cudaMemset(p.scal, 0, sizeof(double) * HS_SCAL_DOUBLES(nprob));
+    if (e == cudaSuccess && ndev > 1) {
+      e = cudaMalloc(&p.mbox, sizeof(double) * hsd_mailbox_doubles());
+      if (e == cudaSuccess) e = cudaMemset(p.mbox, 0, sizeof(double) * hsd_mailbox_doubles());
+      for (int q = 0; q < ndev && e == cudaSuccess; ++q) {
+        if (devices[q] == p.device) continue;
+        int can = 0;
+        e = cudaDeviceCanAccessPeer(&can, p.device, devices[q]);
+        if (e == cudaSuccess && !can) { g_err = "devices cannot access each other's memory (no peer access)"; return bail(HS_ERR_CUDA); }
+        if (e == cudaSuccess) {
+          e = cudaDeviceEnablePeerAccess(devices[q], 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled) { e = cudaSuccess; cudaGetLastError(); }
+        }
+      }
+    }
+    if (e != cudaSuccess) { g_err = std::string("device allocation failed: ") + cudaGetErrorString(e); return bail(HS_ERR_CUDA); }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
   }
-  if (e == cudaSuccess) e = cudaMalloc(&c->scal, sizeof(double) * HS_SCAL_DOUBLES(nprob));
-  if (e == cudaSuccess) e = cudaMemset(c->scal, 0, sizeof(double) * HS_SCAL_DOUBLES(nprob));
-  if (e != cudaSuccess) { g_err = std::string("device allocation failed: ") + cudaGetErrorString(e); return bail(HS_ERR_CUDA); }
+  for (auto& p : c->parts) c->mailboxes.push_back(p.mbox);
   *out = c;
   return HS_OK;
 }
 
+int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob, int device) {
+  return create_impl(out, model, eos, nphase, ncells, nprob, &device, 1);
+}
+
+int hs_create_multi(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, const int* devices, int ndev) {
+  return create_impl(out, model, eos, nphase, ncells, 1, devices, ndev);
+}
+
 int hs_destroy(hs_ctx_t* c) {
   if (!c) return HS_OK;
-  DeviceGuard guard_(c->device);
-  for (int k = 0; k < 2; ++k) { cudaFree(c->Q[k]); cudaFree(c->aux[k]); }
-  cudaFree(c->scal); cudaFree(c->stage); cudaFree(c->dt_hist);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  for (auto& p : c->parts) {
+    DeviceGuard g(p.device);
+    for (int k = 0; k < 2; ++k) { cudaFree(p.Q[k]); cudaFree(p.aux[k]); }
+    cudaFree(p.scal); cudaFree(p.stage); cudaFree(p.mbox);
+    if (p.stream) cudaStreamDestroy(p.stream);
+  }
+  if (!c->parts.empty() && c->dt_hist) { DeviceGuard g(c->parts[0].device); cudaFree(c->dt_hist); }
   delete c;
   return HS_OK;
 }
 
-static int ensure_stage(hs_ctx* c) {
-  if (!c->stage) CU(cudaMalloc(&c->stage, (size_t)c->nvar * c->prob.stride * sizeof(double)));
+static int ensure_stage(hs_ctx* c, Part& p) {
+  if (!p.stage) CU(cudaMalloc(&p.stage, (size_t)c->nvar * p.prob.stride * sizeof(double)));
+  return HS_OK;
+}
+
+static int sync_all(hs_ctx* c) {
+  for (auto& p : c->parts) { PART_ENTER(p); CU(cudaStreamSynchronize(p.stream)); }
   return HS_OK;
 }
 
 static int read_status(hs_ctx* c) {
-  int st = 0;
-  CU(cudaMemcpyAsync(&st, scal_status(c->scal, c->prob.nprob), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  if (st) return fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError");
+  int bad = 0;
+  for (auto& p : c->parts) {
+    PART_ENTER(p);
+    int st = 0;
+    CU(cudaMemcpyAsync(&st, scal_status(p.scal, c->nprob), sizeof(int), cudaMemcpyDeviceToHost, p.stream));
+    CU(cudaStreamSynchronize(p.stream));
+    bad |= st;
+  }
+  if (bad) return fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError");
   return HS_OK;
 }
 
 int hs_upload(hs_ctx_t* c, const double* Q) {
-  CTX_ENTER(c);
-  int rc = HS_OK;
+  if (!c) return fail(HS_ERR_ARG, "null context");
   if (!Q) return fail(HS_ERR_ARG, "null Q");
-  rc = ensure_stage(c); if (rc) return rc;
-  const size_t nq = (size_t)c->nvar * c->prob.stride * sizeof(double);
-  CU(cudaMemcpyAsync(c->stage, Q, nq, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemsetAsync(c->scal, 0, sizeof(double) * HS_SCAL_DOUBLES(c->prob.nprob), c->stream));
   c->n = 0;
-  rc = hsd_aos_to_soa(&c->prob, c->stage, c->Q[0], c->stream); if (rc) return rc;
-  rc = hsd_wave_bounds(&c->prob, c->Q[0], c->aux[0], c->scal, 0, c->stream); if (rc) return rc;
+  for (auto& p : c->parts) {
+    PART_ENTER(p);
+    int rc = ensure_stage(c, p); if (rc) return rc;
+    const size_t nq = (size_t)c->nvar * p.prob.stride * sizeof(double);
+    CU(cudaMemcpyAsync(p.stage, Q + (size_t)p.lo_g * c->nvar, nq, cudaMemcpyHostToDevice, p.stream));
+    CU(cudaMemsetAsync(p.scal, 0, sizeof(double) * HS_SCAL_DOUBLES(c->nprob), p.stream));
+    rc = hsd_aos_to_soa(&p.prob, p.stage, p.Q[0], p.stream); if (rc) return rc;
+    rc = hsd_wave_bounds(&p.prob, p.Q[0], p.aux[0], p.scal, 0, p.stream); if (rc) return rc;
+  }
+  if (c->parts.size() > 1) {   // lambda_max over the slabs (setup path: through the host)
+    double lmax = 0.0;
+    for (auto& p : c->parts) {
+      PART_ENTER(p);
+      double l = 0.0;
+      CU(cudaMemcpyAsync(&l, p.scal, sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+      CU(cudaStreamSynchronize(p.stream));
+      lmax = l > lmax ? l : lmax;
+    }
+    for (auto& p : c->parts) {
+      PART_ENTER(p);
+      CU(cudaMemcpyAsync(p.scal, &lmax, sizeof(double), cudaMemcpyHostToDevice, p.stream));
+      CU(cudaStreamSynchronize(p.stream));
+    }
+  }
   return read_status(c);
 }
 
 int hs_download(hs_ctx_t* c, double* Q) {
-  CTX_ENTER(c);
-  int rc = HS_OK;
+  if (!c) return fail(HS_ERR_ARG, "null context");
   if (!Q) return fail(HS_ERR_ARG, "null Q");
-  rc = ensure_stage(c); if (rc) return rc;
-  rc = hsd_soa_to_aos(&c->prob, c->Q[c->n & 1], c->stage, c->stream); if (rc) return rc;
-  CU(cudaMemcpyAsync(Q, c->stage, (size_t)c->nvar * c->prob.stride * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  return HS_OK;
+  for (auto& p : c->parts) {
+    PART_ENTER(p);
+    int rc = ensure_stage(c, p); if (rc) return rc;
+    rc = hsd_soa_to_aos(&p.prob, p.Q[c->n & 1], p.stage, p.stream); if (rc) return rc;
+    const int64_t owned = (c->parts.size() > 1 ? (p.b - p.a) : c->ncells * c->nprob);
+    const int64_t first = c->parts.size() > 1 ? p.a : 0;
+    CU(cudaMemcpyAsync(Q + (size_t)first * c->nvar, p.stage + (size_t)(first - p.lo_g) * c->nvar, (size_t)owned * c->nvar * sizeof(double),
+                       cudaMemcpyDeviceToHost, p.stream));
+  }
+  return sync_all(c);
 }
 
 int hs_set_time(hs_ctx_t* c, double t, int64_t step) {
-  CTX_ENTER(c);
-  const int64_t np = c->prob.nprob;
+  if (!c) return fail(HS_ERR_ARG, "null context");
+  const int64_t np = c->nprob;
   std::vector<double> tv(np, t);
   std::vector<long long> sv(np, step);
-  CU(cudaMemcpyAsync(hsd_scal_time(c->scal, np, c->n), tv.data(), sizeof(double) * np, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(scal_steps(c->scal, np), sv.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  for (auto& p : c->parts) {
+    PART_ENTER(p);
+    CU(cudaMemcpyAsync(hsd_scal_time(p.scal, np, c->n), tv.data(), sizeof(double) * np, cudaMemcpyHostToDevice, p.stream));
+    CU(cudaMemcpyAsync(scal_steps(p.scal, np), sv.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, p.stream));
+    CU(cudaStreamSynchronize(p.stream));
+  }
   return HS_OK;
 }
 
 int hs_wave_speeds(hs_ctx_t* c, double* eig, double* lambda_max) {
-  CTX_ENTER(c);
-  int rc = HS_OK;
-  const int64_t np = c->prob.nprob;
+  if (!c) return fail(HS_ERR_ARG, "null context");
+  const int64_t np = c->nprob;
   const int cur = (int)(c->n & 1);
+  const int neig = 6 * c->nphase;
   if (eig) {
-    const size_t ne = (size_t)6 * c->prob.nphase * c->prob.stride * sizeof(double);
-    double* d_eig = nullptr;
-    CU(cudaMalloc(&d_eig, ne));
-    // recompute into the current slot (same values: the sweep is deterministic and max is exact)
-    rc = wave_bounds_impl(&c->prob, c->Q[cur], c->aux[cur], c->scal, (int)(c->n % 3), d_eig, c->stream);
-    if (rc == HS_OK && cudaMemcpyAsync(eig, d_eig, ne, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = fail(HS_ERR_CUDA, "eig download failed");
-    cudaStreamSynchronize(c->stream);
-    cudaFree(d_eig);
-    if (rc) return rc;
+    for (auto& p : c->parts) {
+      PART_ENTER(p);
+      DevBufRaw d_eig, d_scal;   // the sweep runs against a scratch scalar block: the context's lambda slots stay untouched
+      CU(d_eig.alloc((size_t)neig * p.prob.stride));
+      CU(d_scal.alloc((size_t)HS_SCAL_DOUBLES(np)));
+      CU(cudaMemsetAsync(d_scal.p, 0, sizeof(double) * HS_SCAL_DOUBLES(np), p.stream));
+      int rc = wave_bounds_impl(&p.prob, p.Q[cur], p.aux[cur], d_scal.p, 0, d_eig.p, p.stream); if (rc) return rc;
+      const int64_t owned = (c->parts.size() > 1 ? (p.b - p.a) : c->ncells * np);
+      const int64_t first = c->parts.size() > 1 ? p.a : 0;
+      CU(cudaMemcpyAsync(eig + (size_t)first * neig, d_eig.p + (size_t)(first - p.lo_g) * neig, (size_t)owned * neig * sizeof(double),
+                         cudaMemcpyDeviceToHost, p.stream));
+      CU(cudaStreamSynchronize(p.stream));
+    }
   }
   if (lambda_max) {
-    CU(cudaMemcpyAsync(lambda_max, hsd_scal_lambda_cur(c->scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    Part& p = c->parts[0];
+    PART_ENTER(p);
+    CU(cudaMemcpyAsync(lambda_max, hsd_scal_lambda_cur(p.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p.stream));
+    CU(cudaStreamSynchronize(p.stream));
   }
   return read_status(c);
 }
 
 static int enqueue_step(hs_ctx* c, int flux, double cfl, double dx, double t_end, double* hist, int64_t hist_k, int64_t hist_cap) {
   const int a = (int)(c->n & 1), b = a ^ 1;
-  int rc = hsd_step(&c->prob, flux, cfl, dx, t_end, c->n, c->Q[a], c->aux[a], c->Q[b], c->aux[b], c->scal,
-                    hist, hist_k, hist_cap, 0, c->stream);
-  if (rc == HS_OK) c->n += 1;
-  return rc;
+  const int ndev = (int)c->parts.size();
+  for (int r = 0; r < ndev; ++r) {
+    Part& p = c->parts[r];
+    PART_ENTER(p);
+    int rc = hsd_step(&p.prob, flux, cfl, dx, t_end, c->n, p.Q[a], p.aux[a], p.Q[b], p.aux[b], p.scal, r == 0 ? hist : nullptr, hist_k,
+                      hist_cap, p.ghost, p.stream);
+    if (rc) return rc;
+  }
+  if (ndev > 1) {   // halo cells + max(lambda) over the slabs: one peer-memory kernel per device
+    c->xseq += 1;
+    for (int r = 0; r < ndev; ++r) {
+      Part& p = c->parts[r];
+      PART_ENTER(p);
+      int rc = hsd_exchange_p2p(&p.prob, p.Q[b], p.aux[b], hsd_scal_lambda_next(p.scal, 1, c->n), c->mailboxes.data(), r, ndev, c->xseq,
+                                p.stream);
+      if (rc) return rc;
+    }
+  }
+  c->n += 1;
+  return HS_OK;
 }
 
 static int ensure_hist(hs_ctx* c, int64_t cap) {
+  Part& p = c->parts[0];
+  PART_ENTER(p);
   if (c->hist_cap >= cap && c->dt_hist) return HS_OK;
   if (c->dt_hist) { cudaFree(c->dt_hist); c->dt_hist = nullptr; }
-  CU(cudaMalloc(&c->dt_hist, sizeof(double) * cap * c->prob.nprob));
+  CU(cudaMalloc(&c->dt_hist, sizeof(double) * cap * c->nprob));
   c->hist_cap = cap;
   return HS_OK;
 }
 
 int hs_step(hs_ctx_t* c, int flux, double cfl, double dx, double* dt_out) {
-  CTX_ENTER(c);
-  int rc = HS_OK;
-  rc = ensure_hist(c, 1); if (rc) return rc;
-  const int64_t np = c->prob.nprob;
+  if (!c) return fail(HS_ERR_ARG, "null context");
+  int rc = ensure_hist(c, 1); if (rc) return rc;
+  const int64_t np = c->nprob;
   rc = enqueue_step(c, flux, cfl, dx, 1.0e300, c->dt_hist, 0, 1); if (rc) return rc;
-  if (dt_out) CU(cudaMemcpyAsync(dt_out, c->dt_hist, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+  if (dt_out) {
+    Part& p = c->parts[0];
+    PART_ENTER(p);
+    CU(cudaMemcpyAsync(dt_out, c->dt_hist, sizeof(double) * np, cudaMemcpyDeviceToHost, p.stream));
+  }
   return read_status(c);
 }
 
 int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64_t max_steps, double* t_io,
                int64_t* step_io, double* dt_hist) {
-  CTX_ENTER(c);
-  int rc = HS_OK;
+  if (!c) return fail(HS_ERR_ARG, "null context");
   if (max_steps < 0) return fail(HS_ERR_ARG, "max_steps < 0");
-  const int64_t np = c->prob.nprob;
-  if (t_io) CU(cudaMemcpyAsync(hsd_scal_time(c->scal, np, c->n), t_io, sizeof(double) * np, cudaMemcpyHostToDevice, c->stream));
-  if (step_io) CU(cudaMemcpyAsync(scal_steps(c->scal, np), step_io, sizeof(long long) * np, cudaMemcpyHostToDevice, c->stream));
+  const int64_t np = c->nprob;
+  for (auto& p : c->parts) {
+    PART_ENTER(p);
+    if (t_io) CU(cudaMemcpyAsync(hsd_scal_time(p.scal, np, c->n), t_io, sizeof(double) * np, cudaMemcpyHostToDevice, p.stream));
+    if (step_io) CU(cudaMemcpyAsync(scal_steps(p.scal, np), step_io, sizeof(long long) * np, cudaMemcpyHostToDevice, p.stream));
+  }
+  Part& p0 = c->parts[0];
   double* hist = nullptr;
   if (dt_hist && max_steps > 0) {
-    rc = ensure_hist(c, max_steps); if (rc) return rc;
-    CU(cudaMemsetAsync(c->dt_hist, 0, sizeof(double) * max_steps * np, c->stream));
+    int rc = ensure_hist(c, max_steps); if (rc) return rc;
+    PART_ENTER(p0);
+    CU(cudaMemsetAsync(c->dt_hist, 0, sizeof(double) * max_steps * np, p0.stream));
     hist = c->dt_hist;
   }
   std::vector<double> tv(np);
@@ -409,18 +535,25 @@ int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64
   const int64_t batch = 32;
   while (done < max_steps) {
     // all problems finished?  (the kernels are no-ops past t_end, so over-launching is harmless)
-    CU(cudaMemcpyAsync(tv.data(), hsd_scal_time(c->scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    {
+      PART_ENTER(p0);
+      CU(cudaMemcpyAsync(tv.data(), hsd_scal_time(p0.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p0.stream));
+      CU(cudaStreamSynchronize(p0.stream));
+    }
     bool any = false;
     for (int64_t i = 0; i < np; ++i) if (tv[i] < t_end) { any = true; break; }
     if (!any) break;
     const int64_t m = (max_steps - done < batch) ? (max_steps - done) : batch;
-    for (int64_t k = 0; k < m; ++k) { rc = enqueue_step(c, flux, cfl, dx, t_end, hist, done + k, max_steps); if (rc) return rc; }
+    for (int64_t k = 0; k < m; ++k) { int rc = enqueue_step(c, flux, cfl, dx, t_end, hist, done + k, max_steps); if (rc) return rc; }
     done += m;
   }
-  if (t_io) CU(cudaMemcpyAsync(t_io, hsd_scal_time(c->scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
-  if (step_io) CU(cudaMemcpyAsync(step_io, scal_steps(c->scal, np), sizeof(long long) * np, cudaMemcpyDeviceToHost, c->stream));
-  if (hist) CU(cudaMemcpyAsync(dt_hist, c->dt_hist, sizeof(double) * max_steps * np, cudaMemcpyDeviceToHost, c->stream));
+  {
+    PART_ENTER(p0);
+    if (t_io) CU(cudaMemcpyAsync(t_io, hsd_scal_time(p0.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p0.stream));
+    if (step_io) CU(cudaMemcpyAsync(step_io, scal_steps(p0.scal, np), sizeof(long long) * np, cudaMemcpyDeviceToHost, p0.stream));
+    if (hist) CU(cudaMemcpyAsync(dt_hist, c->dt_hist, sizeof(double) * max_steps * np, cudaMemcpyDeviceToHost, p0.stream));
+  }
+  int rc = sync_all(c); if (rc) return rc;
   return read_status(c);
 }
 

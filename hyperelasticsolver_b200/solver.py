@@ -25,12 +25,22 @@ class Solver:
     problems of `ncells` cells.  One instance replaces the body of `while t < T` (main.jl:202-227).
     """
 
-    def __init__(self, eos, ncells, nprob=1, model=L.MPH30, device=0):
+    def __init__(self, eos, ncells, nprob=1, model=L.MPH30, device=0, devices=None):
+        """devices=[0, 1, ...]: slab-decompose ONE grid over several GPUs of this process (hs_create_multi);
+        results are bit-identical to the single-device solver."""
         self.model, self.nvar = model, L.NVAR[model]
         self.ncells, self.nprob, self.device = int(ncells), int(nprob), int(device)
         self._ctx = C.c_void_p()
         self._eos = L.eos_array(eos, model)
-        L.check(L.lib().hs_create(C.byref(self._ctx), model, self._eos, L.NPHASE[model], self.ncells, self.nprob, self.device))
+        if devices is not None and len(devices) > 1:
+            if self.nprob != 1:
+                raise ValueError("several devices: one slab-decomposed grid (nprob == 1)")
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            L.check(L.lib().hs_create_multi(C.byref(self._ctx), model, self._eos, L.NPHASE[model], self.ncells, devs, len(devices)))
+        else:
+            if devices:
+                self.device = int(devices[0])
+            L.check(L.lib().hs_create(C.byref(self._ctx), model, self._eos, L.NPHASE[model], self.ncells, self.nprob, self.device))
 
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):

@@ -99,10 +99,17 @@ mutable struct Solver
   nvar::Int; ncells::Int; nprob::Int
 end
 
-function Solver(eos::Tuple{Barton2009,Barton2009}, ncells::Integer; nprob::Integer=1, device::Integer=0)
+# devices = [0, 1, ..., 7]: one grid slab-decomposed over several GPUs of this process (hs_create_multi)
+function Solver(eos::Tuple{Barton2009,Barton2009}, ncells::Integer; nprob::Integer=1, device::Integer=0, devices::Vector{<:Integer}=Int[])
   ref = Ref{Ptr{Cvoid}}(C_NULL); e = eosvec(eos)
-  GC.@preserve e check(ccall((:hs_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Barton2009}, Cint, Int64, Int64, Cint),
-      ref, HS_MODEL_MPH30, e, 2, ncells, nprob, device))
+  if length(devices) > 1
+    d = Vector{Cint}(devices)
+    GC.@preserve e d check(ccall((:hs_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Barton2009}, Cint, Int64, Ptr{Cint}, Cint),
+        ref, HS_MODEL_MPH30, e, 2, ncells, d, length(d)))
+  else
+    GC.@preserve e check(ccall((:hs_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Barton2009}, Cint, Int64, Int64, Cint),
+        ref, HS_MODEL_MPH30, e, 2, ncells, nprob, device))
+  end
   s = Solver(ref[], 30, ncells, nprob)
   finalizer(destroy!, s)
   return s

@@ -139,3 +139,38 @@ def test_stateless_calls_keep_current_device(gpu):
     assert torch.cuda.current_device() == 1
     assert float((x + 1).sum()) == 8.0
     torch.cuda.set_device(0)
+
+
+@pytest.mark.parametrize("model", ["mph30", "sp13"])
+def test_single_process_multi_device_context(gpu, oracle, model):
+    """hs_create_multi: one host process (the Julia-driver situation), one grid slab-decomposed over the
+    GPUs it can see, exchange by the peer-memory kernel.  Must be bit-identical to the one-GPU context."""
+    import torch
+    ndev = min(torch.cuda.device_count(), 4)
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    hs = gpu
+    if model == "mph30":
+        eos = (hs.Barton2009(), hs.Barton2009()); hm = hs.MPH30
+        Ql, Qr = hs.initial_states(eos, 6)
+    else:
+        eos = hs.Barton2009(); hm = hs.SP13
+        Ql, Qr = hs.hyperelasticity.initial_states(eos, 2)
+    nx, steps = 1003, 40          # odd size: unequal slabs
+    Q0 = hs.initial_condition(Ql, Qr, nx)
+    with hs.Solver(eos, nx, model=hm, device=0) as s1:
+        s1.upload(Q0); h1 = s1.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=steps, record_dt=True)
+        Q1 = s1.download(); lam1, eig1 = s1.wave_speeds(full=True)
+    with hs.Solver(eos, nx, model=hm, devices=list(range(ndev))) as s2:
+        s2.upload(Q0); h2 = s2.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=steps, record_dt=True)
+        Q2 = s2.download(); lam2, eig2 = s2.wave_speeds(full=True)
+        assert np.array_equal(h1, h2) and np.array_equal(Q1, Q2)
+        assert np.array_equal(lam1, lam2) and np.array_equal(eig1, eig2)
+        assert s2.steps[0] == steps and s2.t[0] == s1.t[0]
+        # a second upload restarts cleanly (exchange sequence numbers keep increasing), t_end semantics hold
+        s2.upload(Q0); s2.advance(float(h1[0, :7].sum()) * 0.999, "hll", 0.6, 1.0 / nx)
+        assert s2.steps[0] == 7
+        Qh, dt = s2.step_host(Q0, None, "hll", 0.6, 1.0 / nx)
+    with hs.Solver(eos, nx, model=hm, device=0) as s1:
+        Qh1, dt1 = s1.step_host(Q0, None, "hll", 0.6, 1.0 / nx)
+    assert np.array_equal(Qh, Qh1) and dt[0] == dt1[0]
