@@ -62,7 +62,7 @@ SIGNATURES = {
     "hs_last_error": (C.c_char_p, []),
     "hs_device_count": (C.c_int, []),
     "hs_create": (C.c_int, [C.POINTER(_vp), C.c_int, _eosp, C.c_int, _i64, _i64, C.c_int]),
-    "hs_create_multi": (C.c_int, [C.POINTER(_vp), C.c_int, _eosp, C.c_int, _i64, C.POINTER(C.c_int), C.c_int]),
+    "hs_create_multi": (C.c_int, [C.POINTER(_vp), C.c_int, _eosp, C.c_int, _i64, _i64, C.POINTER(C.c_int), C.c_int]),
     "hs_destroy": (C.c_int, [_vp]),
     "hs_upload": (C.c_int, [_vp, _vp]),
     "hs_download": (C.c_int, [_vp, _vp]),

@@ -246,30 +246,37 @@ double* hsd_scal_status(double* scal, int64_t nprob) { return scal + HS_SCAL_SLO
 // kernel per device followed by one k_exchange_p2p per device (peer access, no NCCL).
 // ---------------------------------------------------------------------------------------------
 namespace {
-struct Part {                 // one slab on one device
+struct Part {                 // one slab (or one share of an ensemble) on one device
   int device = 0;
   cudaStream_t stream = nullptr;
-  hsd_problem_t prob;         // ncells = local cells (halo cells included)
-  int64_t a = 0, b = 0;       // owned global cells [a, b)
-  int64_t lo_g = 0;           // global index of local cell 0
+  hsd_problem_t prob;         // slab: ncells = local cells (halo included), nprob = 1; ensemble share: nprob = local problems
+  int64_t a = 0, b = 0;       // slab: owned global cells [a, b);  ensemble share: owned problems [a, b)
+  int64_t lo_g = 0;           // slab: global index of local cell 0
   int ghost = 0;
   double* Q[2] = {nullptr, nullptr};
   double* aux[2] = {nullptr, nullptr};
   double* scal = nullptr;
   double* stage = nullptr;    // AoS staging, nvar * local cells
-  double* mbox = nullptr;     // exchange mailbox (multi-device only)
+  double* mbox = nullptr;     // exchange mailbox (slab mode only)
+  double* dt_hist = nullptr;  // grown on demand
+  int64_t hist_cap = 0;
 };
 }  // namespace
 
 struct hs_ctx {
   int model = 0, nvar = 0, nphase = 0;
   int64_t ncells = 0, nprob = 0;
+  bool slabs = false;         // several devices share ONE grid (halo exchange); otherwise they share the problems
   std::vector<Part> parts;
   std::vector<void*> mailboxes;
-  double* dt_hist = nullptr;  // on parts[0].device, grown on demand
-  int64_t hist_cap = 0;
   int64_t n = 0;              // launch counter since the last upload (selects buffers and scalar slots)
   uint64_t xseq = 0;          // exchange sequence number (never reused)
+  // host range (in cells / in problems) a part reads and writes
+  int64_t first_cell(const Part& p) const { return slabs ? p.lo_g : p.a * ncells; }
+  int64_t owned_first(const Part& p) const { return slabs ? p.a : p.a * ncells; }
+  int64_t owned_cells(const Part& p) const { return slabs ? p.b - p.a : (p.b - p.a) * ncells; }
+  int64_t first_prob(const Part& p) const { return slabs ? 0 : p.a; }
+  int64_t nprob_local(const Part& p) const { return p.prob.nprob; }
 };
 
 #define PART_ENTER(p)                                              \
@@ -282,35 +289,43 @@ static int create_impl(hs_ctx_t** out, int model, const hs_barton2009_t* eos, in
   *out = nullptr;
   if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
   if (ndev < 1 || ndev > MBOX_MAXR || !devices) return fail(HS_ERR_ARG, "1..8 devices");
-  if (ndev > 1 && nprob != 1) return fail(HS_ERR_ARG, "several devices: one slab-decomposed grid (nprob == 1)");
   hsd_problem_t whole;
   int rc = hsd_problem_init(&whole, model, eos, nphase, ncells, nprob);
   if (rc) return rc;
-  if (ndev > 1 && ncells / ndev < 3) return fail(HS_ERR_ARG, "slabs too small: need >= 3 cells per device");
+  const bool slabs = ndev > 1 && nprob == 1;
+  if (slabs && ncells / ndev < 3) return fail(HS_ERR_ARG, "slabs too small: need >= 3 cells per device");
+  if (ndev > 1 && !slabs && nprob < ndev) return fail(HS_ERR_ARG, "fewer problems than devices");
   hs_ctx* c = new hs_ctx();
   c->model = model; c->nvar = model == HS_MODEL_MPH30 ? 30 : 13; c->nphase = nphase; c->ncells = ncells; c->nprob = nprob;
+  c->slabs = slabs;
   c->parts.resize(ndev);
   auto bail = [&](int code) { hs_destroy(c); return code; };
   for (int r = 0; r < ndev; ++r) {
     Part& p = c->parts[r];
     p.device = devices[r];
-    p.a = ncells * r / ndev; p.b = ncells * (r + 1) / ndev;                  // same partition as slab.py::slab_bounds
-    p.lo_g = p.a - (r > 0 ? 1 : 0);
-    const int64_t hi_g = p.b + (r < ndev - 1 ? 1 : 0);
-    p.ghost = (r > 0 ? 1 : 0) | (r < ndev - 1 ? 2 : 0);
-    rc = hsd_problem_init(&p.prob, model, eos, nphase, hi_g - p.lo_g, nprob);
+    if (slabs) {
+      p.a = ncells * r / ndev; p.b = ncells * (r + 1) / ndev;                  // same partition as slab.py::slab_bounds
+      p.lo_g = p.a - (r > 0 ? 1 : 0);
+      const int64_t hi_g = p.b + (r < ndev - 1 ? 1 : 0);
+      p.ghost = (r > 0 ? 1 : 0) | (r < ndev - 1 ? 2 : 0);
+      rc = hsd_problem_init(&p.prob, model, eos, nphase, hi_g - p.lo_g, 1);
+    } else {
+      p.a = nprob * r / ndev; p.b = nprob * (r + 1) / ndev;                    // problems [a, b)
+      rc = hsd_problem_init(&p.prob, model, eos, nphase, ncells, p.b - p.a);
+    }
     if (rc) return bail(rc);
     DeviceGuard g(p.device);
     if (!g.ok) return bail(fail(HS_ERR_CUDA, "cudaSetDevice failed"));
     cudaError_t e = cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking);
     const size_t nq = (size_t)c->nvar * p.prob.stride * sizeof(double), nb = (size_t)HS_NAUX(model) * p.prob.stride * sizeof(double);
+    const size_t ns = sizeof(double) * HS_SCAL_DOUBLES(p.prob.nprob);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
       e = cudaMalloc(&p.Q[k], nq);
       if (e == cudaSuccess) e = cudaMalloc(&p.aux[k], nb);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&p.scal, sizeof(double) * HS_SCAL_DOUBLES(nprob));
-    if (e == cudaSuccess) e = cudaMemset(p.scal, 0, sizeof(double) * HS_SCAL_DOUBLES(nprob));
-    if (e == cudaSuccess && ndev > 1) {
+    if (e == cudaSuccess) e = cudaMalloc(&p.scal, ns);
+    if (e == cudaSuccess) e = cudaMemset(p.scal, 0, ns);
+    if (e == cudaSuccess && slabs) {
       e = cudaMalloc(&p.mbox, sizeof(double) * hsd_mailbox_doubles());
       if (e == cudaSuccess) e = cudaMemset(p.mbox, 0, sizeof(double) * hsd_mailbox_doubles());
       for (int q = 0; q < ndev && e == cudaSuccess; ++q) {
@@ -324,8 +339,8 @@ static int create_impl(hs_ctx_t** out, int model, const hs_barton2009_t* eos, in
         }
       }
     }
-    if (e != cudaSuccess) { g_err = std::string("device allocation failed: ") + cudaGetErrorString(e); return bail(HS_ERR_CUDA); }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { g_err = std::string("device allocation failed: ") + cudaGetErrorString(e); return bail(HS_ERR_CUDA); }
   }
   for (auto& p : c->parts) c->mailboxes.push_back(p.mbox);
   *out = c;
@@ -336,8 +351,9 @@ int hs_create(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase,
   return create_impl(out, model, eos, nphase, ncells, nprob, &device, 1);
 }
 
-int hs_create_multi(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, const int* devices, int ndev) {
-  return create_impl(out, model, eos, nphase, ncells, 1, devices, ndev);
+int hs_create_multi(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob,
+                    const int* devices, int ndev) {
+  return create_impl(out, model, eos, nphase, ncells, nprob, devices, ndev);
 }
 
 int hs_destroy(hs_ctx_t* c) {
@@ -345,10 +361,9 @@ int hs_destroy(hs_ctx_t* c) {
   for (auto& p : c->parts) {
     DeviceGuard g(p.device);
     for (int k = 0; k < 2; ++k) { cudaFree(p.Q[k]); cudaFree(p.aux[k]); }
-    cudaFree(p.scal); cudaFree(p.stage); cudaFree(p.mbox);
+    cudaFree(p.scal); cudaFree(p.stage); cudaFree(p.mbox); cudaFree(p.dt_hist);
     if (p.stream) cudaStreamDestroy(p.stream);
   }
-  if (!c->parts.empty() && c->dt_hist) { DeviceGuard g(c->parts[0].device); cudaFree(c->dt_hist); }
   delete c;
   return HS_OK;
 }
@@ -368,7 +383,7 @@ static int read_status(hs_ctx* c) {
   for (auto& p : c->parts) {
     PART_ENTER(p);
     int st = 0;
-    CU(cudaMemcpyAsync(&st, scal_status(p.scal, c->nprob), sizeof(int), cudaMemcpyDeviceToHost, p.stream));
+    CU(cudaMemcpyAsync(&st, scal_status(p.scal, p.prob.nprob), sizeof(int), cudaMemcpyDeviceToHost, p.stream));
     CU(cudaStreamSynchronize(p.stream));
     bad |= st;
   }
@@ -384,12 +399,12 @@ int hs_upload(hs_ctx_t* c, const double* Q) {
     PART_ENTER(p);
     int rc = ensure_stage(c, p); if (rc) return rc;
     const size_t nq = (size_t)c->nvar * p.prob.stride * sizeof(double);
-    CU(cudaMemcpyAsync(p.stage, Q + (size_t)p.lo_g * c->nvar, nq, cudaMemcpyHostToDevice, p.stream));
-    CU(cudaMemsetAsync(p.scal, 0, sizeof(double) * HS_SCAL_DOUBLES(c->nprob), p.stream));
+    CU(cudaMemcpyAsync(p.stage, Q + (size_t)c->first_cell(p) * c->nvar, nq, cudaMemcpyHostToDevice, p.stream));
+    CU(cudaMemsetAsync(p.scal, 0, sizeof(double) * HS_SCAL_DOUBLES(p.prob.nprob), p.stream));
     rc = hsd_aos_to_soa(&p.prob, p.stage, p.Q[0], p.stream); if (rc) return rc;
     rc = hsd_wave_bounds(&p.prob, p.Q[0], p.aux[0], p.scal, 0, p.stream); if (rc) return rc;
   }
-  if (c->parts.size() > 1) {   // lambda_max over the slabs (setup path: through the host)
+  if (c->slabs) {   // lambda_max over the slabs (setup path: through the host)
     double lmax = 0.0;
     for (auto& p : c->parts) {
       PART_ENTER(p);
@@ -414,21 +429,20 @@ int hs_download(hs_ctx_t* c, double* Q) {
     PART_ENTER(p);
     int rc = ensure_stage(c, p); if (rc) return rc;
     rc = hsd_soa_to_aos(&p.prob, p.Q[c->n & 1], p.stage, p.stream); if (rc) return rc;
-    const int64_t owned = (c->parts.size() > 1 ? (p.b - p.a) : c->ncells * c->nprob);
-    const int64_t first = c->parts.size() > 1 ? p.a : 0;
-    CU(cudaMemcpyAsync(Q + (size_t)first * c->nvar, p.stage + (size_t)(first - p.lo_g) * c->nvar, (size_t)owned * c->nvar * sizeof(double),
-                       cudaMemcpyDeviceToHost, p.stream));
+    const int64_t first = c->owned_first(p);
+    CU(cudaMemcpyAsync(Q + (size_t)first * c->nvar, p.stage + (size_t)(first - c->first_cell(p)) * c->nvar,
+                       (size_t)c->owned_cells(p) * c->nvar * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
   }
   return sync_all(c);
 }
 
 int hs_set_time(hs_ctx_t* c, double t, int64_t step) {
   if (!c) return fail(HS_ERR_ARG, "null context");
-  const int64_t np = c->nprob;
-  std::vector<double> tv(np, t);
-  std::vector<long long> sv(np, step);
   for (auto& p : c->parts) {
     PART_ENTER(p);
+    const int64_t np = p.prob.nprob;
+    std::vector<double> tv(np, t);
+    std::vector<long long> sv(np, step);
     CU(cudaMemcpyAsync(hsd_scal_time(p.scal, np, c->n), tv.data(), sizeof(double) * np, cudaMemcpyHostToDevice, p.stream));
     CU(cudaMemcpyAsync(scal_steps(p.scal, np), sv.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, p.stream));
     CU(cudaStreamSynchronize(p.stream));
@@ -438,44 +452,43 @@ int hs_set_time(hs_ctx_t* c, double t, int64_t step) {
 
 int hs_wave_speeds(hs_ctx_t* c, double* eig, double* lambda_max) {
   if (!c) return fail(HS_ERR_ARG, "null context");
-  const int64_t np = c->nprob;
   const int cur = (int)(c->n & 1);
   const int neig = 6 * c->nphase;
-  if (eig) {
-    for (auto& p : c->parts) {
-      PART_ENTER(p);
+  for (auto& p : c->parts) {
+    PART_ENTER(p);
+    const int64_t np = p.prob.nprob;
+    if (eig) {
       DevBufRaw d_eig, d_scal;   // the sweep runs against a scratch scalar block: the context's lambda slots stay untouched
       CU(d_eig.alloc((size_t)neig * p.prob.stride));
       CU(d_scal.alloc((size_t)HS_SCAL_DOUBLES(np)));
       CU(cudaMemsetAsync(d_scal.p, 0, sizeof(double) * HS_SCAL_DOUBLES(np), p.stream));
       int rc = wave_bounds_impl(&p.prob, p.Q[cur], p.aux[cur], d_scal.p, 0, d_eig.p, p.stream); if (rc) return rc;
-      const int64_t owned = (c->parts.size() > 1 ? (p.b - p.a) : c->ncells * np);
-      const int64_t first = c->parts.size() > 1 ? p.a : 0;
-      CU(cudaMemcpyAsync(eig + (size_t)first * neig, d_eig.p + (size_t)(first - p.lo_g) * neig, (size_t)owned * neig * sizeof(double),
-                         cudaMemcpyDeviceToHost, p.stream));
+      const int64_t first = c->owned_first(p);
+      CU(cudaMemcpyAsync(eig + (size_t)first * neig, d_eig.p + (size_t)(first - c->first_cell(p)) * neig,
+                         (size_t)c->owned_cells(p) * neig * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
       CU(cudaStreamSynchronize(p.stream));
     }
-  }
-  if (lambda_max) {
-    Part& p = c->parts[0];
-    PART_ENTER(p);
-    CU(cudaMemcpyAsync(lambda_max, hsd_scal_lambda_cur(p.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p.stream));
-    CU(cudaStreamSynchronize(p.stream));
+    if (lambda_max && (!c->slabs || &p == &c->parts[0])) {
+      CU(cudaMemcpyAsync(lambda_max + c->first_prob(p), hsd_scal_lambda_cur(p.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p.stream));
+      CU(cudaStreamSynchronize(p.stream));
+    }
   }
   return read_status(c);
 }
 
-static int enqueue_step(hs_ctx* c, int flux, double cfl, double dx, double t_end, double* hist, int64_t hist_k, int64_t hist_cap) {
+// hist_cap > 0: every part records the step's dt of its problems at dt_hist[prob * hist_cap + hist_k]
+static int enqueue_step(hs_ctx* c, int flux, double cfl, double dx, double t_end, int64_t hist_k, int64_t hist_cap) {
   const int a = (int)(c->n & 1), b = a ^ 1;
   const int ndev = (int)c->parts.size();
   for (int r = 0; r < ndev; ++r) {
     Part& p = c->parts[r];
     PART_ENTER(p);
-    int rc = hsd_step(&p.prob, flux, cfl, dx, t_end, c->n, p.Q[a], p.aux[a], p.Q[b], p.aux[b], p.scal, r == 0 ? hist : nullptr, hist_k,
-                      hist_cap, p.ghost, p.stream);
+    double* hist = (hist_cap > 0 && (!c->slabs || r == 0)) ? p.dt_hist : nullptr;
+    int rc = hsd_step(&p.prob, flux, cfl, dx, t_end, c->n, p.Q[a], p.aux[a], p.Q[b], p.aux[b], p.scal, hist, hist_k, hist_cap, p.ghost,
+                      p.stream);
     if (rc) return rc;
   }
-  if (ndev > 1) {   // halo cells + max(lambda) over the slabs: one peer-memory kernel per device
+  if (c->slabs) {   // halo cells + max(lambda) over the slabs: one peer-memory kernel per device
     c->xseq += 1;
     for (int r = 0; r < ndev; ++r) {
       Part& p = c->parts[r];
@@ -490,25 +503,33 @@ static int enqueue_step(hs_ctx* c, int flux, double cfl, double dx, double t_end
 }
 
 static int ensure_hist(hs_ctx* c, int64_t cap) {
-  Part& p = c->parts[0];
-  PART_ENTER(p);
-  if (c->hist_cap >= cap && c->dt_hist) return HS_OK;
-  if (c->dt_hist) { cudaFree(c->dt_hist); c->dt_hist = nullptr; }
-  CU(cudaMalloc(&c->dt_hist, sizeof(double) * cap * c->nprob));
-  c->hist_cap = cap;
+  for (auto& p : c->parts) {
+    PART_ENTER(p);
+    if (p.hist_cap < cap || !p.dt_hist) {
+      if (p.dt_hist) { cudaFree(p.dt_hist); p.dt_hist = nullptr; }
+      CU(cudaMalloc(&p.dt_hist, sizeof(double) * cap * p.prob.nprob));
+      p.hist_cap = cap;
+    }
+    CU(cudaMemsetAsync(p.dt_hist, 0, sizeof(double) * cap * p.prob.nprob, p.stream));
+  }
+  return HS_OK;
+}
+
+// gather per-problem doubles (dt history columns, ...) from the parts into a host array
+static int gather_hist(hs_ctx* c, double* dst, int64_t cap) {
+  for (auto& p : c->parts) {
+    if (c->slabs && &p != &c->parts[0]) continue;
+    PART_ENTER(p);
+    CU(cudaMemcpyAsync(dst + (size_t)c->first_prob(p) * cap, p.dt_hist, sizeof(double) * cap * p.prob.nprob, cudaMemcpyDeviceToHost, p.stream));
+  }
   return HS_OK;
 }
 
 int hs_step(hs_ctx_t* c, int flux, double cfl, double dx, double* dt_out) {
   if (!c) return fail(HS_ERR_ARG, "null context");
   int rc = ensure_hist(c, 1); if (rc) return rc;
-  const int64_t np = c->nprob;
-  rc = enqueue_step(c, flux, cfl, dx, 1.0e300, c->dt_hist, 0, 1); if (rc) return rc;
-  if (dt_out) {
-    Part& p = c->parts[0];
-    PART_ENTER(p);
-    CU(cudaMemcpyAsync(dt_out, c->dt_hist, sizeof(double) * np, cudaMemcpyDeviceToHost, p.stream));
-  }
+  rc = enqueue_step(c, flux, cfl, dx, 1.0e300, 0, 1); if (rc) return rc;
+  if (dt_out) { rc = gather_hist(c, dt_out, 1); if (rc) return rc; }
   return read_status(c);
 }
 
@@ -516,43 +537,42 @@ int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64
                int64_t* step_io, double* dt_hist) {
   if (!c) return fail(HS_ERR_ARG, "null context");
   if (max_steps < 0) return fail(HS_ERR_ARG, "max_steps < 0");
-  const int64_t np = c->nprob;
   for (auto& p : c->parts) {
     PART_ENTER(p);
-    if (t_io) CU(cudaMemcpyAsync(hsd_scal_time(p.scal, np, c->n), t_io, sizeof(double) * np, cudaMemcpyHostToDevice, p.stream));
-    if (step_io) CU(cudaMemcpyAsync(scal_steps(p.scal, np), step_io, sizeof(long long) * np, cudaMemcpyHostToDevice, p.stream));
+    const int64_t np = p.prob.nprob, off = c->first_prob(p);
+    if (t_io) CU(cudaMemcpyAsync(hsd_scal_time(p.scal, np, c->n), t_io + off, sizeof(double) * np, cudaMemcpyHostToDevice, p.stream));
+    if (step_io) CU(cudaMemcpyAsync(scal_steps(p.scal, np), step_io + off, sizeof(long long) * np, cudaMemcpyHostToDevice, p.stream));
   }
-  Part& p0 = c->parts[0];
-  double* hist = nullptr;
-  if (dt_hist && max_steps > 0) {
-    int rc = ensure_hist(c, max_steps); if (rc) return rc;
-    PART_ENTER(p0);
-    CU(cudaMemsetAsync(c->dt_hist, 0, sizeof(double) * max_steps * np, p0.stream));
-    hist = c->dt_hist;
-  }
-  std::vector<double> tv(np);
+  const bool record = dt_hist && max_steps > 0;
+  if (record) { int rc = ensure_hist(c, max_steps); if (rc) return rc; }
+  std::vector<double> tv;
   int64_t done = 0;
   const int64_t batch = 32;
   while (done < max_steps) {
     // all problems finished?  (the kernels are no-ops past t_end, so over-launching is harmless)
-    {
-      PART_ENTER(p0);
-      CU(cudaMemcpyAsync(tv.data(), hsd_scal_time(p0.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p0.stream));
-      CU(cudaStreamSynchronize(p0.stream));
-    }
     bool any = false;
-    for (int64_t i = 0; i < np; ++i) if (tv[i] < t_end) { any = true; break; }
+    for (auto& p : c->parts) {
+      if (c->slabs && &p != &c->parts[0]) continue;
+      PART_ENTER(p);
+      const int64_t np = p.prob.nprob;
+      tv.resize(np);
+      CU(cudaMemcpyAsync(tv.data(), hsd_scal_time(p.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p.stream));
+      CU(cudaStreamSynchronize(p.stream));
+      for (int64_t i = 0; i < np && !any; ++i) any = tv[i] < t_end;
+    }
     if (!any) break;
     const int64_t m = (max_steps - done < batch) ? (max_steps - done) : batch;
-    for (int64_t k = 0; k < m; ++k) { int rc = enqueue_step(c, flux, cfl, dx, t_end, hist, done + k, max_steps); if (rc) return rc; }
+    for (int64_t k = 0; k < m; ++k) { int rc = enqueue_step(c, flux, cfl, dx, t_end, done + k, record ? max_steps : 0); if (rc) return rc; }
     done += m;
   }
-  {
-    PART_ENTER(p0);
-    if (t_io) CU(cudaMemcpyAsync(t_io, hsd_scal_time(p0.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p0.stream));
-    if (step_io) CU(cudaMemcpyAsync(step_io, scal_steps(p0.scal, np), sizeof(long long) * np, cudaMemcpyDeviceToHost, p0.stream));
-    if (hist) CU(cudaMemcpyAsync(dt_hist, c->dt_hist, sizeof(double) * max_steps * np, cudaMemcpyDeviceToHost, p0.stream));
+  for (auto& p : c->parts) {
+    if (c->slabs && &p != &c->parts[0]) continue;
+    PART_ENTER(p);
+    const int64_t np = p.prob.nprob, off = c->first_prob(p);
+    if (t_io) CU(cudaMemcpyAsync(t_io + off, hsd_scal_time(p.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p.stream));
+    if (step_io) CU(cudaMemcpyAsync(step_io + off, scal_steps(p.scal, np), sizeof(long long) * np, cudaMemcpyDeviceToHost, p.stream));
   }
+  if (record) { int rc = gather_hist(c, dt_hist, max_steps); if (rc) return rc; }
   int rc = sync_all(c); if (rc) return rc;
   return read_status(c);
 }

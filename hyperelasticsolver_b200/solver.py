@@ -26,17 +26,17 @@ class Solver:
     """
 
     def __init__(self, eos, ncells, nprob=1, model=L.MPH30, device=0, devices=None):
-        """devices=[0, 1, ...]: slab-decompose ONE grid over several GPUs of this process (hs_create_multi);
-        results are bit-identical to the single-device solver."""
+        """devices=[0, 1, ...]: spread the work over several GPUs of this process (hs_create_multi): one grid
+        (nprob == 1) is slab-decomposed, an ensemble (nprob > 1) is shared out by problems; results are
+        bit-identical to the single-device solver."""
         self.model, self.nvar = model, L.NVAR[model]
         self.ncells, self.nprob, self.device = int(ncells), int(nprob), int(device)
         self._ctx = C.c_void_p()
         self._eos = L.eos_array(eos, model)
         if devices is not None and len(devices) > 1:
-            if self.nprob != 1:
-                raise ValueError("several devices: one slab-decomposed grid (nprob == 1)")
             devs = (C.c_int * len(devices))(*[int(d) for d in devices])
-            L.check(L.lib().hs_create_multi(C.byref(self._ctx), model, self._eos, L.NPHASE[model], self.ncells, devs, len(devices)))
+            L.check(L.lib().hs_create_multi(C.byref(self._ctx), model, self._eos, L.NPHASE[model], self.ncells, self.nprob, devs,
+                                            len(devices)))
         else:
             if devices:
                 self.device = int(devices[0])

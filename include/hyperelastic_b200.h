@@ -56,13 +56,16 @@ int hs_device_count(void);
  * `device`.  eos: nphase blocks (2 for MPH30, 1 for SP13). */
 int hs_create(hs_ctx_t** ctx, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells,
               int64_t nprob, int device);
-/* The same for ONE grid slab-decomposed over `ndev` (<= 8) devices of this process that can access each
- * other's memory (NVLink / PCIe peer access): contiguous slabs with one halo cell per side; every step is
- * one fused kernel per device plus one small peer-memory exchange kernel per device (halo cells and
- * max(lambda), no NCCL).  All other calls (upload / step / advance / download ...) are unchanged and the
- * results are bit-identical to the single-device context.  This is what a single-process driver such as
- * `julia main.jl` uses to run the 2^28-cell case on an 8-GPU box. */
-int hs_create_multi(hs_ctx_t** ctx, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, const int* devices, int ndev);
+/* The same over `ndev` (<= 8) devices of this process -- what a single-process driver such as
+ * `julia main.jl` uses to reach an 8-GPU box.  All other calls (upload / step / advance / download ...)
+ * are unchanged and the results are bit-identical to the single-device context.
+ *   nprob == 1: ONE grid slab-decomposed over the devices (contiguous slabs, one halo cell per side); the
+ *     devices must be able to access each other's memory (NVLink / PCIe peer access).  Every step is one fused
+ *     kernel per device plus one small peer-memory exchange kernel per device (halo cells and max(lambda)),
+ *     no NCCL, no host synchronisation.
+ *   nprob  > 1: the independent problems are shared out over the devices; no exchange at all. */
+int hs_create_multi(hs_ctx_t** ctx, int model, const hs_barton2009_t* eos, int nphase, int64_t ncells, int64_t nprob,
+                    const int* devices, int ndev);
 int hs_destroy(hs_ctx_t* ctx);
 
 /* Q0 of main.jl:101,179: (nvar, ncells, nprob) column-major.  Upload also evaluates the

@@ -99,13 +99,14 @@ mutable struct Solver
   nvar::Int; ncells::Int; nprob::Int
 end
 
-# devices = [0, 1, ..., 7]: one grid slab-decomposed over several GPUs of this process (hs_create_multi)
+# devices = [0, 1, ..., 7]: several GPUs of this process (hs_create_multi): one grid is slab-decomposed,
+# an ensemble (nprob > 1) is shared out by problems
 function Solver(eos::Tuple{Barton2009,Barton2009}, ncells::Integer; nprob::Integer=1, device::Integer=0, devices::Vector{<:Integer}=Int[])
   ref = Ref{Ptr{Cvoid}}(C_NULL); e = eosvec(eos)
   if length(devices) > 1
     d = Vector{Cint}(devices)
-    GC.@preserve e d check(ccall((:hs_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Barton2009}, Cint, Int64, Ptr{Cint}, Cint),
-        ref, HS_MODEL_MPH30, e, 2, ncells, d, length(d)))
+    GC.@preserve e d check(ccall((:hs_create_multi, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Barton2009}, Cint, Int64, Int64, Ptr{Cint}, Cint),
+        ref, HS_MODEL_MPH30, e, 2, ncells, nprob, d, length(d)))
   else
     GC.@preserve e check(ccall((:hs_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Barton2009}, Cint, Int64, Int64, Cint),
         ref, HS_MODEL_MPH30, e, 2, ncells, nprob, device))

@@ -174,3 +174,28 @@ def test_single_process_multi_device_context(gpu, oracle, model):
     with hs.Solver(eos, nx, model=hm, device=0) as s1:
         Qh1, dt1 = s1.step_host(Q0, None, "hll", 0.6, 1.0 / nx)
     assert np.array_equal(Qh, Qh1) and dt[0] == dt1[0]
+
+
+def test_single_process_multi_device_ensemble(gpu, oracle):
+    """hs_create_multi with nprob > 1: problems shared out over the GPUs of the process, per-problem dt."""
+    import torch
+    ndev = min(torch.cuda.device_count(), 4)
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    hs = gpu
+    rng = np.random.default_rng(17)
+    eos = (hs.Barton2009(), hs.Barton2009())
+    nprob, nx = 7, 90
+    Ql = hs.prim2cons_mph(eos, random_mph_prims(rng, nprob, spread=0.03)); Qr = hs.prim2cons_mph(eos, random_mph_prims(rng, nprob, spread=0.03))
+    Q0 = np.stack([hs.initial_condition(Ql[i], Qr[i], nx) for i in range(nprob)])
+    t_end = 0.01
+    out = []
+    for devs in (None, list(range(ndev))):
+        with hs.Solver(eos, nx, nprob=nprob, devices=devs) as sol:
+            sol.upload(Q0)
+            dt1 = sol.step("hll", 0.6, 1.0 / nx)
+            hist = sol.advance(t_end, "hll", 0.6, 1.0 / nx, max_steps=300, record_dt=True)
+            out.append((sol.download(), dt1.copy(), hist, sol.t.copy(), sol.steps.copy(), sol.wave_speeds()))
+    for x, y in zip(out[0], out[1]):
+        assert np.array_equal(x, y)
+    assert len(set(out[0][4].tolist())) > 1          # problems really finish at different step counts
