@@ -86,7 +86,7 @@ SIGNATURES = {
                            _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
     "hsd_halo": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "hsd_mailbox_doubles": (C.c_int, []),
-    "hsd_exchange_p2p": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_uint64, _vp]),
+    "hsd_exchange_p2p": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_uint64, _vp, _vp]),
     "hsd_scal_lambda_next": (_vp, [_vp, _i64, _i64]),
     "hsd_scal_lambda_cur": (_vp, [_vp, _i64, _i64]),
     "hsd_scal_time": (_vp, [_vp, _i64, _i64]),

@@ -218,7 +218,7 @@ int hsd_halo(const hsd_problem_t* p, double* Q, double* aux, double* left, doubl
 int hsd_mailbox_doubles(void) { return 2 * MBOX_STRIDE; }
 
 int hsd_exchange_p2p(const hsd_problem_t* p, double* Q, double* aux, double* lam_slot, void* const* mailboxes, int rank, int world,
-                     uint64_t seq, void* stream) {
+                     uint64_t seq, double* scal, void* stream) {
   if (p->nprob != 1) return fail(HS_ERR_ARG, "halo exchange applies to a single slab-decomposed grid");
   if (world < 1 || world > MBOX_MAXR || rank < 0 || rank >= world) return fail(HS_ERR_ARG, "p2p exchange supports 1..8 ranks on one node");
   if (seq == 0) return fail(HS_ERR_ARG, "seq must start at 1 (mailboxes are zero-initialised)");
@@ -226,8 +226,10 @@ int hsd_exchange_p2p(const hsd_problem_t* p, double* Q, double* aux, double* lam
   if (nvar + naux > MBOX_MAXW) return fail(HS_ERR_ARG, "mailbox too small");
   PeerPtrs pp;
   for (int i = 0; i < MBOX_MAXR; ++i) pp.p[i] = i < world ? static_cast<double*>(mailboxes[i]) : nullptr;
+  static const unsigned long long timeout_ns = 1000000000ull * (unsigned long long)(std::getenv("HS_EXCHANGE_TIMEOUT_S") ? std::atoi(std::getenv("HS_EXCHANGE_TIMEOUT_S")) : 20);
   k_exchange_p2p<<<1, 64, 0, (cudaStream_t)stream>>>(Q, aux, reinterpret_cast<unsigned long long*>(lam_slot), pp, p->stride,
-                                                    (int)p->ncells, nvar, naux, rank, world, (unsigned long long)seq);
+                                                    (int)p->ncells, nvar, naux, rank, world, (unsigned long long)seq,
+                                                    scal_status(scal, p->nprob), timeout_ns);
   g_launches++;
   CU(cudaGetLastError());
   return HS_OK;
@@ -387,6 +389,7 @@ static int read_status(hs_ctx* c) {
     CU(cudaStreamSynchronize(p.stream));
     bad |= st;
   }
+  if (bad & 2) return fail(HS_ERR_CUDA, "peer-memory exchange timed out: a device of the context stopped stepping");
   if (bad) return fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError");
   return HS_OK;
 }
@@ -494,7 +497,7 @@ static int enqueue_step(hs_ctx* c, int flux, double cfl, double dx, double t_end
       Part& p = c->parts[r];
       PART_ENTER(p);
       int rc = hsd_exchange_p2p(&p.prob, p.Q[b], p.aux[b], hsd_scal_lambda_next(p.scal, 1, c->n), c->mailboxes.data(), r, ndev, c->xseq,
-                                p.stream);
+                                p.scal, p.stream);
       if (rc) return rc;
     }
   }

@@ -635,9 +635,15 @@ constexpr int MBOX_MAXW = 40, MBOX_MAXR = 8;
 constexpr int MBOX_STRIDE = 2 * MBOX_MAXW + 2 * MBOX_MAXR;    // doubles per parity
 struct PeerPtrs { double* p[MBOX_MAXR]; };
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(64) k_exchange_p2p(double* Q, double* aux, unsigned long long* lam_slot, const PeerPtrs peers,
                                                      long long stride, int ncells, int nvar, int naux, int rank, int world,
-                                                     unsigned long long seq) {
+                                                     unsigned long long seq, int* status, unsigned long long timeout_ns) {
   const int v = threadIdx.x, W = nvar + naux;
   const int par = (int)(seq & 1ull);
   const size_t base = (size_t)par * MBOX_STRIDE;
@@ -658,7 +664,11 @@ __global__ void __launch_bounds__(64) k_exchange_p2p(double* Q, double* aux, uns
   double* mine = peers.p[rank] + base;
   if (v < world) {
     volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(mine + 2 * MBOX_MAXW + MBOX_MAXR);
-    while (f[v] != seq) { }
+    const unsigned long long t0 = global_timer_ns();
+    while (f[v] != seq) {
+      // a peer that died never posts: give up instead of hanging the GPU, and say so in the status word
+      if (global_timer_ns() - t0 > timeout_ns) { atomicOr(status, 2); break; }
+    }
   }
   __threadfence_system();
   __syncthreads();

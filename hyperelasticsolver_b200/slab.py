@@ -86,10 +86,10 @@ class CudaKernels:
     def mailbox_doubles(self):
         return int(self._lib.hsd_mailbox_doubles())
 
-    def exchange_p2p(self, prob, Q, aux, lam_slot, peer_ptrs, rank, world, seq):
+    def exchange_p2p(self, prob, Q, aux, lam_slot, peer_ptrs, rank, world, seq, scal):
         arr = (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in peer_ptrs])
         L.check(self._lib.hsd_exchange_p2p(C.byref(prob), Q.data_ptr(), aux.data_ptr(), lam_slot.data_ptr(), arr, rank, world, seq,
-                                           self._stream()))
+                                           scal.data_ptr(), self._stream()))
 
     def launches(self):
         return int(self._lib.hs_kernel_launch_count())
@@ -121,7 +121,10 @@ class _Base:
         return self._lam[self.n % 3].cpu().numpy().copy()
 
     def check_status(self):
-        if int(self._status.cpu()[0]) != 0:
+        st = int(self._status.cpu()[0])
+        if st & 2:
+            raise L.HyperelasticError(L.HS_ERR_CUDA, "peer-memory exchange timed out: another rank stopped stepping")
+        if st != 0:
             raise L.DomainError(L.HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError")
 
 
@@ -274,7 +277,7 @@ class SlabSolver(_Base):
         if self.exchange == "p2p-kernel":
             self._xseq += 1
             self.k.exchange_p2p(self.prob, self.Q[b], self.aux[b], self._lam[(self.n + 1) % 3], self._peer_ptrs, self.rank, self.world,
-                                self._xseq)
+                                self._xseq, self.scal)
         else:
             self._halo_exchange(b)
             self._allreduce_lambda((self.n + 1) % 3)

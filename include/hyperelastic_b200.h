@@ -171,10 +171,12 @@ int hsd_halo(const hsd_problem_t* p, double* Q, double* aux, double* left, doubl
  * (hsd_mailbox_doubles() doubles each, zero-initialised, allocated as peer-accessible / symmetric
  * memory, e.g. torch.distributed._symmetric_memory); lam_slot = hsd_scal_lambda_next(scal, 1, n) of the
  * step just enqueued; seq = 1, 2, 3, ... identical on all ranks and never reused.  <= 8 ranks, one node.
- * Results are bit-identical to hsd_halo + all-reduce(max). */
+ * Results are bit-identical to hsd_halo + all-reduce(max).  A peer that never posts (crashed rank) does not
+ * hang the GPU: after HS_EXCHANGE_TIMEOUT_S seconds (default 20) the kernel gives up and sets bit 1 of the
+ * status word of `scal`. */
 int hsd_mailbox_doubles(void);
 int hsd_exchange_p2p(const hsd_problem_t* p, double* Q, double* aux, double* lam_slot, void* const* mailboxes, int rank, int world,
-                     uint64_t seq, void* stream);
+                     uint64_t seq, double* scal, void* stream);
 /* address (device pointer) of the lambda_max slot that step n WRITES, as doubles [nprob]:
  * the buffer to all-reduce(max) across ranks between step n and n+1 */
 double* hsd_scal_lambda_next(double* scal, int64_t nprob, int64_t n);

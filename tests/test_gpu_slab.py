@@ -199,3 +199,10 @@ def test_single_process_multi_device_ensemble(gpu, oracle):
     for x, y in zip(out[0], out[1]):
         assert np.array_equal(x, y)
     assert len(set(out[0][4].tolist())) > 1          # problems really finish at different step counts
+
+
+def test_exchange_gives_up_on_a_dead_peer(gpu):
+    import subprocess
+    env = dict(os.environ, HS_EXCHANGE_TIMEOUT_S="1")
+    out = subprocess.run([sys.executable, os.path.join(HERE, "exchange_timeout_check.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "EXCHANGE-TIMEOUT-OK" in out.stdout, out.stdout[-1000:] + out.stderr[-3000:]
