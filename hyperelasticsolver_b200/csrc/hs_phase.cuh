@@ -119,8 +119,13 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   const double r = rho * eos.inv_rho0;
   double rA, rB, rC, irC;
   if (GEN) {
+    // generic exponents: one log, then one exp per exponent that is not a small integer (the shipped
+    // alternative copper set, main.jl:133, has alpha = 1: r itself)
     const double L = log(r);
-    rA = exp(eos.ea * L); rB = exp(eos.eb * L); rC = exp(eos.eg * L); irC = 1.0 / rC;
+    rA = (eos.ea == 1.0) ? r : ((eos.ea == 2.0) ? r * r : exp(eos.ea * L));
+    rB = (eos.eb == 3.0) ? r * r * r : ((eos.eb == 2.0) ? r * r : exp(eos.eb * L));
+    rC = (eos.eg == 2.0) ? r * r : ((eos.eg == 1.0) ? r : exp(eos.eg * L));
+    irC = 1.0 / rC;
   } else {
     const double ir = eos.rho0 * rs;
     rA = r; rB = r * r * r; rC = r * r; irC = ir * ir;
