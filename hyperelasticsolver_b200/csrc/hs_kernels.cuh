@@ -110,7 +110,7 @@ __device__ __forceinline__ void noncons_column(const PhaseState& st, const doubl
 #pragma unroll
   for (int k = 0; k < 3; ++k) { uo[k] = __shfl_xor_sync(FULL, st.u[k], 1); so[k] = __shfl_xor_sync(FULL, st.sig1[k], 1); }
   const double uI[3] = {0.5 * st.u[0] + 0.5 * uo[0], 0.5 * st.u[1] + 0.5 * uo[1], 0.5 * st.u[2] + 0.5 * uo[2]};  // :213
-  const double inv = 1.0 / (st.T + To);
+  const double inv = hs_rcp(st.T + To);
   const double sI[3] = {(To * st.sig1[0] + st.T * so[0]) * inv, (To * st.sig1[1] + st.T * so[1]) * inv,
                         (To * st.sig1[2] + st.T * so[2]) * inv};                                            // :217
   c[0] = uI[0];                                                                                              // :223
@@ -137,7 +137,7 @@ __device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const d
 #pragma unroll
   for (int k = 0; k < 3; ++k) { uo[k] = __shfl_xor_sync(FULL, st.u[k], 1); so[k] = __shfl_xor_sync(FULL, st.sig1[k], 1); }
   const double uI[3] = {0.5 * st.u[0] + 0.5 * uo[0], 0.5 * st.u[1] + 0.5 * uo[1], 0.5 * st.u[2] + 0.5 * uo[2]};
-  const double wi = w * (1.0 / (st.T + To));
+  const double wi = w * hs_rcp(st.T + To);
   const double n0 = To * st.sig1[0] + st.T * so[0], n1 = To * st.sig1[1] + st.T * so[1], n2 = To * st.sig1[2] + st.T * so[2];
   acc[0] += w * uI[0];
   acc[2] += wi * n0; acc[3] += wi * n1; acc[4] += wi * n2;
@@ -214,7 +214,7 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
       s_r = fmax(0.0, fmax(hi_m, hi_r));
     }
     if (s_out) { s_out[0] = s_l; s_out[1] = s_r; }
-    const double inv_ds = 1.0 / (s_r - s_l);
+    const double inv_ds = hs_rcp(s_r - s_l);
     const double k_q = s_l * s_r * inv_ds;
     if (MPH) {
       double acc[15];
@@ -351,10 +351,16 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 
   const double lam_cur = __longlong_as_double((long long)lam_bits);
   const bool active = t_cur < g.t_end;                   // while t < T, main.jl:202
-  const double dt = g.cfl * g.dx / lam_cur;              // main.jl:212
-  const double dtdx = dt / g.dx;                         // main.jl:225
-  const double lambda = g.dx / dt;                       // main.jl:223
-  const double upd = (FLUX == FLUX_HLL) ? dtdx : 1.0 / lambda;  // main.jl:59 / :40
+  // dt and the update factor are per-problem scalars: one thread does the (IEEE, correctly rounded)
+  // divisions, the block reads them after the next barrier
+  double* sc = red + 8;                                  // [dt, update factor, dx/dt]
+  if (tid == 0) {
+    const double dt0 = g.cfl * g.dx / lam_cur;           // main.jl:212
+    const double lambda0 = g.dx / dt0;                   // main.jl:223
+    sc[0] = dt0;
+    sc[1] = (FLUX == FLUX_HLL) ? dt0 / g.dx : 1.0 / lambda0;   // main.jl:225,59 / :40
+    sc[2] = lambda0;
+  }
 
   if (!active) {  // this problem already reached t_end: carry the state through unchanged
     if (own_interior || own_frozen) {
@@ -400,6 +406,8 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
       if (!flux_is_zero(j)) Fs[flux_row(j) * T + tid] = f[j];
   }
   __syncthreads();
+
+  const double dt = sc[0], upd = sc[1], lambda = sc[2];
 
   // ---- face between cell l-1 and cell l (hll / lxf, NumFluxes.jl) ---------------------------
   const int tl = (l >= 1) ? tid - NPH : tid;   // halo threads evaluate a dummy face against themselves

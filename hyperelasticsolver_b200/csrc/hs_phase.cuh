@@ -60,11 +60,42 @@ inline EosDev make_eos_dev(const EosAbi& e) {
 }
 inline bool eos_is_default_exponents(const EosAbi& e) { return e.alpha == 1.0 && e.beta == 3.0 && e.gamma == 2.0; }
 
+// Branch-free reciprocal / reciprocal square root / square root for the hot path: hardware seed
+// (MUFU.RCP64H / MUFU.RSQ64H, ~20 good bits) + two Newton steps in FMA form (20 -> 40 -> 80 bits,
+// i.e. <= 1-2 ulp).  The CUDA library versions are correctly rounded but carry a slow-path call with
+// register shuffling around every use; every argument here is an O(1) positive quantity of an
+// admissible state (inadmissible states are flagged separately through PhaseState::bad).
+HS_HD double hs_rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
+#endif
+}
 HS_HD double hs_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
-  return rsqrt(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-(x * y), y, 1.0);      // 1 - x y^2
+  y = fma(0.5 * y, e, y);
+  e = fma(-(x * y), y, 1.0);
+  return fma(0.5 * y, e, y);
 #else
   return 1.0 / sqrt(x);
+#endif
+}
+HS_HD double hs_sqrt(double x) {
+#ifdef __CUDA_ARCH__
+  const double y = hs_rsqrt(x);
+  const double sq = x * y;
+  return fma(0.5 * y, fma(-sq, sq, x), sq);   // one more correction on the product
+#else
+  return sqrt(x);
 #endif
 }
 
@@ -93,7 +124,7 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   const double C31 = A[3] * A[7] - A[6] * A[4], C32 = A[6] * A[1] - A[0] * A[7], C33 = A[0] * A[4] - A[3] * A[1];
   // (A is column-major: A[i+3j]; C_ij = cofactor of A_ij.)  det by first row: A11 C11 + A12 C12 + A13 C13
   const double detA = A[0] * C11 + A[3] * C12 + A[6] * C13;
-  const double ia = 1.0 / alpha;
+  const double ia = hs_rcp(alpha);
   const double x = detA * (ia * ia * ia) * eos.inv_rho0;      // det(A/alpha)/rho0 = rho^2
   s.bad = !(x > 0.0);
   const double rs = hs_rsqrt(x);                              // 1/rho
@@ -125,7 +156,7 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
     rA = (eos.ea == 1.0) ? r : ((eos.ea == 2.0) ? r * r : exp(eos.ea * L));
     rB = (eos.eb == 3.0) ? r * r * r : ((eos.eb == 2.0) ? r * r : exp(eos.eb * L));
     rC = (eos.eg == 2.0) ? r * r : ((eos.eg == 1.0) ? r : exp(eos.eg * L));
-    irC = 1.0 / rC;
+    irC = hs_rcp(rC);
   } else {
     const double ir = eos.rho0 * rs;
     rA = r; rB = r * r * r; rC = r * r; irC = ir * ir;
@@ -219,7 +250,8 @@ HS_HD void sym3_eigs_jacobi(const double* s6, double* ev) {
   ev[2] = fmax(a00, fmax(a11, a22));
 }
 // rare path of sym3_max_abs_eig: full Jacobi solve (accurate for any degeneracy), kept out of line
-HS_HD_COLD double sym3_max_abs_eig_cold(const double* a) {
+HS_HD_COLD double sym3_max_abs_eig_cold(double a0, double a1, double a2, double a3, double a4, double a5) {
+  const double a[6] = {a0, a1, a2, a3, a4, a5};   // by value: the hot path must not spill the tensor to local memory
   double ev[3];
   sym3_eigs_jacobi(a, ev);
   return fmax(fabs(ev[0]), fabs(ev[2]));
@@ -266,7 +298,7 @@ HS_HD double sym3_max_abs_eig(const double* a) {
     }
     return q + p * mu;
   }
-  return sym3_max_abs_eig_cold(a);
+  return sym3_max_abs_eig_cold(a[0], a[1], a[2], a[3], a[4], a[5]);
 }
 
 // Symmetrised acoustic tensor for n = (1,0,0):
@@ -338,7 +370,7 @@ HS_HD void phase_acoustic_sym_n(const EosDev& eos, const PhaseState& s, const do
 HS_HD double phase_cmax(const EosDev& eos, const PhaseState& s) {
   double S6[6];
   phase_acoustic_sym(eos, s, S6);
-  return sqrt(sym3_max_abs_eig(S6));
+  return hs_sqrt(sym3_max_abs_eig(S6));
 }
 
 }  // namespace hs
