@@ -26,6 +26,12 @@ namespace hs {
 #define HS_NODE_UNROLL 1
 #endif
 
+// single-phase: 1 = the step reads / writes the cached 1/rho + stress rows (aux rows 2..5), 0 = it recovers the
+// state at its head instead (less traffic, more arithmetic) -- tuning knob
+#ifndef HS_SP_USE_CACHE
+#define HS_SP_USE_CACHE 1
+#endif
+
 constexpr int MODEL_SP13 = 0, MODEL_MPH30 = 1;
 constexpr int FLUX_LXF = 0, FLUX_HLL = 1;
 constexpr unsigned FULL = 0xffffffffu;
@@ -325,7 +331,8 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
   // cached bounds) before anything consumes them, so their latencies overlap.
   const unsigned long long lam_bits = __ldg(g.lam + (size_t)g.cur * g.nprob + prob);
   const double t_cur = __ldg(g.tt + (size_t)g.cur * g.nprob + prob);
-  double rin[15], lo_in_r = 0.0, hi_in_r = 0.0, ax[MODEL == MODEL_SP13 ? 4 : 1];
+  double rin[15], lo_in_r = 0.0, hi_in_r = 0.0, ax[(MODEL == MODEL_SP13) ? 4 : 1];
+  constexpr bool SPC = (MODEL == MODEL_SP13) && (HS_SP_USE_CACHE != 0);   // single-phase: use the cached 1/rho + stress row
   if (MODEL == MODEL_MPH30) {
 #pragma unroll
     for (int j = 0; j < 15; ++j) rin[j] = __ldg(g.Qin + (size_t)(15 * ph + j) * g.stride + gi);
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     for (int v = 0; v < 13; ++v) rin[sp_slot(v)] = __ldg(g.Qin + (size_t)v * g.stride + gi);
   }
   if (ph == 0) { lo_in_r = __ldg(g.aux_in + gi); hi_in_r = __ldg(g.aux_in + g.stride + gi); }
-  if (MODEL == MODEL_SP13) {
+  if (SPC) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) ax[r] = __ldg(g.aux_in + (size_t)(2 + r) * g.stride + gi);
   }
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
         for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = Rs[sp_slot(v) * T + tid];
       }
       if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
-      if (MODEL == MODEL_SP13) {
+      if (SPC) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) g.aux_out[(size_t)(2 + r) * g.stride + gi] = ax[r];
       }
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 
   int bad = 0;
   // ---- per-cell physical flux (flux_mph, HyperelasticityMPh.jl:140-175) -----------------------
-  if (MODEL == MODEL_SP13) {
+  if (SPC) {
     double f[15];
     sp_flux_cached(rin, ax[0], ax + 1, f);   // state recovery was done by the previous step's CFL sweep
 #pragma unroll
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     if (own_interior) {
       bad |= sn.bad;
       if (ph == 0) { g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n; }
-      if (MODEL == MODEL_SP13) {
+      if (SPC) {
         g.aux_out[(size_t)2 * g.stride + gi] = sn.inv_den;
 #pragma unroll
         for (int r = 0; r < 3; ++r) g.aux_out[(size_t)(3 + r) * g.stride + gi] = sn.sig1[r];
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
       lamv = fmax(fabs(lo_n), fabs(hi_n));
     } else if (own_frozen) {
       if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
-      if (MODEL == MODEL_SP13) {
+      if (SPC) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) g.aux_out[(size_t)(2 + r) * g.stride + gi] = ax[r];
       }
