@@ -73,18 +73,26 @@ int* scal_status(double* s, int64_t nprob) { return reinterpret_cast<int*>(s + H
 #endif
 constexpr int T_STEP_MPH = HS_T_STEP_MPH, T_STEP_SP = HS_T_STEP_SP, T_FACE = 64;
 
-template <int MODEL, int FLUX, bool GEN, int T>
-int launch_step_t(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
+template <int MODEL, int FLUX, bool GEN, int T, bool SAME>
+int launch_step_s(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t smem = step_smem_bytes<MODEL, T>();
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(k_step<MODEL, FLUX, GEN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_step<MODEL, FLUX, GEN, T, SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  k_step<MODEL, FLUX, GEN, T><<<(unsigned)nblocks, T, smem, st>>>(a);
+  k_step<MODEL, FLUX, GEN, T, SAME><<<(unsigned)nblocks, T, smem, st>>>(a);
   g_launches++;
   CU(cudaGetLastError());
   return HS_OK;
+}
+
+template <int MODEL, int FLUX, bool GEN, int T>
+int launch_step_t(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
+  // one thread per cell (single phase) always reads phase 0; two phases: specialise when the EoS blocks are identical
+  const bool same = MODEL == MODEL_SP13 || std::memcmp(&a.eos.e[0], &a.eos.e[1], sizeof(EosDev)) == 0;
+  if (MODEL == MODEL_SP13 || same) return launch_step_s<MODEL, FLUX, GEN, T, true>(a, nblocks, st);
+  return launch_step_s<MODEL, FLUX, GEN, T, (MODEL == MODEL_SP13)>(a, nblocks, st);
 }
 
 template <int MODEL, int T>

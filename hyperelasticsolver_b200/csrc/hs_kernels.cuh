@@ -304,7 +304,9 @@ template <int MODEL, int T> constexpr size_t step_smem_bytes() {
 #ifndef HS_MINB_SP
 #define HS_MINB_SP 4
 #endif
-template <int MODEL, int FLUX, bool GEN, int T>
+// SAME: both phases share one equation of state (the shipped configuration, main.jl:134): the EoS constants
+// are then uniform kernel parameters (constant-bank operands) instead of per-lane constant loads.
+template <int MODEL, int FLUX, bool GEN, int T, bool SAME>
 __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MINB_SP)) k_step(const StepArgs g) {
   using MT = ModelTraits<MODEL>;
   constexpr int NPH = MT::NPH, CPB = T / NPH, J0 = MT::J0;
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
   const int c = tile * (CPB - 2) + l;
   const bool valid = c < g.ncells;
   const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
-  const EosDev& eos = g.eos.e[ph];
+  const EosDev& eos = g.eos.e[SAME ? 0 : ph];
 
   // Issue every global load of the block back to back (two per-problem scalars, the tile, the
   // cached bounds) before anything consumes them, so their latencies overlap.
