@@ -78,6 +78,8 @@ SIGNATURES = {
     "hs_get_eigvals": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _vp, _i64, C.c_int]),
     "hs_hll": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "hs_lxf": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, C.c_int]),
+    "hs_selftest_math": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_int]),
+    "hs_selftest_eig": (C.c_int, [_vp, _vp, _i64, C.c_int]),
     "hsd_problem_init": (C.c_int, [C.POINTER(HsdProblem), C.c_int, _eosp, C.c_int, _i64, _i64]),
     "hsd_aos_to_soa": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp]),
     "hsd_soa_to_aos": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp]),

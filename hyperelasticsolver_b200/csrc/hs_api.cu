@@ -698,6 +698,38 @@ int faceop(int model, int flux, const hs_barton2009_t* eos, int nphase, const do
 }  // namespace
 
 extern "C" {
+// device self-test hooks (tests/ only): the hot path's branch-free reciprocal / rsqrt / sqrt and its
+// largest-eigenvalue solve evaluated on caller data
+int hs_selftest_math(const double* x, double* rcp, double* rsq, double* sq, int64_t n, int device) {
+  if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return fail(HS_ERR_CUDA, "cudaSetDevice failed");
+  DevBuf dx, d1, d2, d3;
+  CU(dx.alloc(n)); CU(d1.alloc(n)); CU(d2.alloc(n)); CU(d3.alloc(n));
+  CU(cudaMemcpy(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  k_selftest_math<<<(unsigned)((n + 127) / 128), 128>>>(dx.p, d1.p, d2.p, d3.p, n);
+  g_launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(rcp, d1.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(rsq, d2.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(sq, d3.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return HS_OK;
+}
+
+int hs_selftest_eig(const double* s6, double* lam_max_abs, int64_t n, int device) {
+  if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return fail(HS_ERR_CUDA, "cudaSetDevice failed");
+  DevBuf di, dout;
+  CU(di.alloc(6 * n)); CU(dout.alloc(n));
+  CU(cudaMemcpy(di.p, s6, sizeof(double) * 6 * n, cudaMemcpyHostToDevice));
+  k_selftest_eig<<<(unsigned)((n + 127) / 128), 128>>>(di.p, dout.p, n);
+  g_launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(lam_max_abs, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return HS_OK;
+}
+
 int hs_cons2prim(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* P, int64_t n, int device) {
   return cellop<OP_CONS2PRIM>(model, eos, nphase, Q, P, n, device);
 }

@@ -858,6 +858,18 @@ __global__ void __launch_bounds__(T) k_faceop(const double* __restrict__ Ql, con
   (void)J0;
 }
 
+// self-test of the branch-free device math (hs_rcp / hs_rsqrt / hs_sqrt / largest eigenvalue) on caller data
+__global__ void k_selftest_math(const double* __restrict__ x, double* rcp, double* rsq, double* sq, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rcp[i] = hs_rcp(x[i]); rsq[i] = hs_rsqrt(x[i]); sq[i] = hs_sqrt(x[i]);
+}
+__global__ void k_selftest_eig(const double* __restrict__ s6, double* out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = sym3_max_abs_eig(s6 + 6 * i);
+}
+
 // full get_eigvals over a Julia-layout batch (HyperelasticityMPh.jl:252-266)
 struct Normal3 { double n[3]; };
 template <int MODEL, bool GEN>

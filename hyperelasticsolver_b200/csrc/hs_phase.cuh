@@ -93,7 +93,8 @@ HS_HD double hs_sqrt(double x) {
 #ifdef __CUDA_ARCH__
   const double y = hs_rsqrt(x);
   const double sq = x * y;
-  return fma(0.5 * y, fma(-sq, sq, x), sq);   // one more correction on the product
+  const double r = fma(0.5 * y, fma(-sq, sq, x), sq);   // one more correction on the product
+  return x > 0.0 ? r : (x == 0.0 ? 0.0 : r);            // sqrt(0) = 0 (the seed is inf there); negative -> NaN
 #else
   return sqrt(x);
 #endif
@@ -282,7 +283,7 @@ HS_HD double sym3_max_abs_eig(const double* a) {
   const double p1 = a[1] * a[1] + a[2] * a[2] + a[4] * a[4];
   const double b0 = a[0] - q, b3 = a[3] - q, b5 = a[5] - q;
   const double p2 = (b0 * b0 + b3 * b3 + b5 * b5 + 2.0 * p1) * (1.0 / 6.0);
-  if (!(p2 > 0.0)) return fabs(q);
+  if (!(p2 > 1e-280)) return fabs(q);   // isotropic tensor (also keeps the flush-to-zero reciprocal-sqrt seed away from denormals)
   const double ip = hs_rsqrt(p2);
   const double p = p2 * ip;
   const double detb = b0 * (b3 * b5 - a[4] * a[4]) - a[1] * (a[1] * b5 - a[4] * a[2]) + a[2] * (a[1] * a[4] - b3 * a[2]);

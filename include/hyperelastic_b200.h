@@ -125,6 +125,11 @@ int hs_hll(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, 
 int hs_lxf(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, const double* Qr, double lambda,
            double* cons, double* dm, double* dp, int64_t n, int device);
 
+/* Device self-test hooks used by tests/: the hot path's branch-free reciprocal / reciprocal square root /
+ * square root (x > 0) and its largest-|eigenvalue| solve of symmetric 3x3 tensors s6 = [11,12,13,22,23,33] (6, n). */
+int hs_selftest_math(const double* x, double* rcp, double* rsq, double* sq, int64_t n, int device);
+int hs_selftest_eig(const double* s6, double* lam_max_abs, int64_t n, int device);
+
 /* ------------------------------------------------------------------------------------------
  * Device-pointer layer (structure-of-arrays, caller-owned device memory and stream): what the
  * one-process-per-GPU driver uses so that halo exchange / allreduce (NCCL through

@@ -309,3 +309,34 @@ def test_get_eigvals_general_normal_and_full_sweep(gpu, oracle):
         Q1 = sol.download()
     ego, _ = oracle.get_eigvals(oe, oracle.MPH30, Q1)
     assert relerr(eig, ego, per_var=False) < 1e-12 and abs(lam[0] - np.abs(ego).max()) < 1e-12 * lam[0]
+
+
+def test_device_math_selftest(gpu):
+    """The hot path's branch-free 1/x, 1/sqrt(x), sqrt(x) (hardware seed + two Newton FMAs) and its Newton
+    largest-eigenvalue solve, evaluated ON THE DEVICE, against numpy."""
+    from hyperelasticsolver_b200 import _lib as L
+    rng = np.random.default_rng(8)
+    x = np.concatenate([10.0 ** rng.uniform(-6, 6, 200000), rng.uniform(0.01, 100.0, 200000), [1.0, 2.0, 4.0, 0.25, 1e-300, 1e300]])
+    rcp = np.empty_like(x); rsq = np.empty_like(x); sq = np.empty_like(x)
+    L.check(L.lib().hs_selftest_math(x.ctypes.data, rcp.ctypes.data, rsq.ctypes.data, sq.ctypes.data, x.size, 0))
+    ulp = lambda got, ref: np.abs(got - ref) / np.spacing(np.abs(ref))
+    assert ulp(rcp, 1.0 / x).max() <= 2.0
+    assert ulp(rsq, 1.0 / np.sqrt(x)).max() <= 2.0
+    assert ulp(sq, np.sqrt(x)).max() <= 2.0
+    z = np.zeros(1); o = [np.empty(1) for _ in range(3)]
+    L.check(L.lib().hs_selftest_math(z.ctypes.data, o[0].ctypes.data, o[1].ctypes.data, o[2].ctypes.data, 1, 0))
+    assert o[2][0] == 0.0                                     # sqrt(0) = 0
+    # largest |eigenvalue|: positive definite, degenerate pairs, indefinite
+    n = 100000
+    S6 = np.empty((n, 6)); ref = np.empty(n)
+    Qs = np.linalg.qr(rng.normal(size=(n, 3, 3)))[0]
+    ev = np.sort(rng.uniform(0.5, 30.0, (n, 3)), axis=1)
+    ev[::3, 1] = ev[::3, 0] * (1 + rng.uniform(0, 1e-6, ev[::3, 0].shape))                 # degenerate shear pair
+    ev[::7, 1] = ev[::7, 2] * (1 - 10.0 ** rng.uniform(-12, -1, ev[::7, 2].shape))          # (near-)degenerate largest pair
+    ev[::11] -= rng.uniform(0, 40.0, (ev[::11].shape[0], 1))                              # indefinite
+    M = np.einsum("nij,nj,nkj->nik", Qs, ev, Qs); M = 0.5 * (M + M.transpose(0, 2, 1))
+    S6[:] = np.stack([M[:, 0, 0], M[:, 0, 1], M[:, 0, 2], M[:, 1, 1], M[:, 1, 2], M[:, 2, 2]], axis=1)
+    ref = np.abs(np.linalg.eigvalsh(M)).max(axis=1)
+    out = np.empty(n)
+    L.check(L.lib().hs_selftest_eig(S6.ctypes.data, out.ctypes.data, n, 0))
+    assert (np.abs(out - ref) / ref).max() < 5e-15
