@@ -340,3 +340,30 @@ def test_device_math_selftest(gpu):
     out = np.empty(n)
     L.check(L.lib().hs_selftest_eig(S6.ctypes.data, out.ctypes.data, n, 0))
     assert (np.abs(out - ref) / ref).max() < 5e-15
+
+
+@pytest.mark.parametrize("tc", [1, 2, 3, 4, 5, 6, 7, 10])
+def test_all_shipped_test_cases(gpu, oracle, tc):
+    """Every Riemann problem of initial_states (HyperelasticityMPh.jl:276-408): first dt against
+    SURVEY.md B.3, then 15 HLL steps against the oracle (tc 1-2 are strongly pre-strained: density 5.0
+    against rho0 = 8.93; tc 1-5 have identical phases, which must stay bit-identical with alpha = 1/2)."""
+    import json, os
+    hs = gpu
+    B = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_appendix_b.json")))["lambda_max_dt_nx1000_cfl06"]
+    eos = (hs.Barton2009(), hs.Barton2009())
+    nx = 1000
+    Ql, Qr = hs.initial_states(eos, tc)
+    Q0 = hs.initial_condition(Ql, Qr, nx)
+    with hs.Solver(eos, nx) as sol:
+        sol.upload(Q0)
+        lam = sol.wave_speeds()[0]
+        assert abs(lam - B[str(tc)][0]) < 1e-13 * lam
+        dt = sol.step("hll", 0.6, 1.0 / nx)[0]
+        assert abs(dt - B[str(tc)][1]) < 1e-13 * dt
+        sol.upload(Q0)
+        sol.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=15)
+        Q = sol.download()
+    ref = oracle.run(None, oracle.MPH30, oracle.HLL, Q0, 0.6, 1.0 / nx, 1e9, 15, nthreads=oracle.hardware_threads())
+    assert ref["status"] == 0 and relerr(Q, ref["Q"]) < 1e-9
+    if tc <= 5:
+        assert np.array_equal(Q[:, :15], Q[:, 15:]) and np.all(Q[:, 0] == 0.5)

@@ -9,8 +9,9 @@ def relerr(a, b, per_var=True):
     if per_var and a.ndim >= 2:
         ax = tuple(range(a.ndim - 1))
         scale = np.maximum(np.abs(b).max(axis=ax), 1e-300)
-        # variables that are identically ~0 (e.g. u1 in a state at rest) are scaled by the global norm
-        scale = np.maximum(scale, 1e-8 * np.abs(b).max())
+        # variables that are identically 0 up to roundoff (e.g. a momentum component of a state at rest) carry
+        # only noise: scale them by the size of the state instead of by their own ~1e-16 magnitude
+        scale = np.maximum(scale, 1e-3 * np.abs(b).max())
         return float((np.abs(a - b).max(axis=ax) / scale).max())
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
