@@ -367,3 +367,15 @@ def test_all_shipped_test_cases(gpu, oracle, tc):
     assert ref["status"] == 0 and relerr(Q, ref["Q"]) < 1e-9
     if tc <= 5:
         assert np.array_equal(Q[:, :15], Q[:, 15:]) and np.all(Q[:, 0] == 0.5)
+
+
+def test_c_abi_from_plain_c(gpu, tmp_path):
+    """examples/abi_smoke.c: the library driven from C (no Python / torch in the process), golden run B.5."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(root, "hyperelasticsolver_b200")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "abi_smoke.c"), "-o", exe,
+                           "-L" + libdir, "-lhyperelastic_b200", "-Wl,-rpath," + libdir, "-lm"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ABI-SMOKE-OK" in out.stdout, out.stdout + out.stderr
