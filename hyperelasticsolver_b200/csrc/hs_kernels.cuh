@@ -104,7 +104,7 @@ __device__ __forceinline__ void column_state(const EosDev& eos, const double* co
 #pragma unroll
   for (int k = 0; k < 9; ++k) A[k] = col[(6 + k) * T];
   const double alpha = (MODEL == MODEL_MPH30) ? col[0] : 1.0;
-  phase_state<GEN>(eos, alpha, m, col[5 * T], A, st);
+  phase_state<GEN, MODEL == MODEL_SP13>(eos, alpha, m, col[5 * T], A, st);
 }
 
 // Column 1 of the non-conservative block of this thread's phase at one state (the other phase's
@@ -208,7 +208,7 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
       for (int k = 0; k < 9; ++k) A[k] = 0.5 * (a[(6 + k) * T] + b[(6 + k) * T]);
       const double alpha = MPH ? 0.5 * (a[0] + b[0]) : 1.0;
       PhaseState sm;
-      phase_state<GEN>(eos, alpha, m, 0.5 * (a[5 * T] + b[5 * T]), A, sm);
+      phase_state<GEN, !MPH>(eos, alpha, m, 0.5 * (a[5 * T] + b[5 * T]), A, sm);
       bad |= sm.bad;
       const double cm = phase_cmax(eos, sm);
       double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     }
     // CFL sweep of the next step (get_eigvals, main.jl:204-211) on the state just produced
     PhaseState sn;
-    phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? qn[0] : 1.0, qn + 2, qn[5], qn + 6, sn);
+    phase_state<GEN, MODEL == MODEL_SP13>(eos, (MODEL == MODEL_MPH30) ? qn[0] : 1.0, qn + 2, qn[5], qn + 6, sn);
     const double cn = phase_cmax(eos, sn);
     double lo_n = sn.u[0] - cn, hi_n = sn.u[0] + cn;
     if (NPH == 2) {

@@ -117,7 +117,10 @@ struct PhaseState {
   int bad;                // 1 where Julia would throw DomainError (sqrt of a negative) or NaN
 };
 
-template <bool GEN>
+// ONE: alpha is the literal 1 (single-phase model) -- its reciprocal and powers fold away at compile time
+// (the reciprocal below is inline PTX, which the compiler cannot fold by itself; rcp(1) = 1 exactly, so
+// the result is bit-identical).
+template <bool GEN, bool ONE = false>
 HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double E, const double* A, PhaseState& s) {
   // cofactors of A:  inv(A) = C^T / det A
   const double C11 = A[4] * A[8] - A[7] * A[5], C12 = A[7] * A[2] - A[1] * A[8], C13 = A[1] * A[5] - A[4] * A[2];
@@ -125,7 +128,8 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   const double C31 = A[3] * A[7] - A[6] * A[4], C32 = A[6] * A[1] - A[0] * A[7], C33 = A[0] * A[4] - A[3] * A[1];
   // (A is column-major: A[i+3j]; C_ij = cofactor of A_ij.)  det by first row: A11 C11 + A12 C12 + A13 C13
   const double detA = A[0] * C11 + A[3] * C12 + A[6] * C13;
-  const double ia = hs_rcp(alpha);
+  const double ia = ONE ? 1.0 : hs_rcp(alpha);
+  if (ONE) alpha = 1.0;
   const double x = detA * (ia * ia * ia) * eos.inv_rho0;      // det(A/alpha)/rho0 = rho^2
   s.bad = !(x > 0.0);
   const double rs = hs_rsqrt(x);                              // 1/rho
