@@ -95,8 +95,52 @@ int launch_step_t(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
   return launch_step_s<MODEL, FLUX, GEN, T, (MODEL == MODEL_SP13)>(a, nblocks, st);
 }
 
+// Single-phase TMA tile pipeline (k_step_sp): every block walks over `kper` tiles, grid-stride.
+template <int FLUX, bool GEN, int T>
+int launch_step_sp(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st) {
+  static bool attr_set = false;   // (one device attribute per kernel instantiation; set on every device it is used on)
+  constexpr size_t smem = step_sp_smem_bytes<T>();
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (!attr_set || !(attr_dev_mask & (1 << (dev & 31)))) {
+    CU(cudaFuncSetAttribute(k_step_sp<FLUX, GEN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true; attr_dev_mask |= 1 << (dev & 31);
+  }
+  const int64_t nblocks = (ntiles + kper - 1) / kper;
+  k_step_sp<FLUX, GEN, T><<<(unsigned)nblocks, T, smem, st>>>(a, kper);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+
+// tiles per block of the pipeline: 8, fewer on grids too small to fill the GPU twice over; HS_SP_TILES=k forces k
+int sp_tiles_per_block(int64_t ntiles) {
+  int64_t k;
+  if (const char* e = std::getenv("HS_SP_TILES")) {
+    k = std::atoi(e);
+    if (k > 64) k = 64;
+  } else {
+    k = ntiles / (2 * 4 * 148);
+    if (k > 8) k = 8;
+  }
+  if (k > ntiles) k = ntiles;
+  if (k < 1) k = 1;
+  return (int)k;
+}
+
 template <int MODEL, int T>
 int launch_step_m(int flux, int gen, const StepArgs& a, int64_t nb, cudaStream_t st) {
+  if (MODEL == MODEL_SP13) {
+    // the pipeline needs 16-byte aligned array bases (any cudaMalloc / torch allocation); HS_SP_TMA=0 forces the plain kernel
+    const char* e = std::getenv("HS_SP_TMA");
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a.Qin) | reinterpret_cast<uintptr_t>(a.aux_in)) & 15u) == 0;
+    if (aligned && !(e && e[0] == '0')) {
+      const int kper = sp_tiles_per_block(nb);
+      if (flux == HS_FLUX_HLL) return gen ? launch_step_sp<FLUX_HLL, true, T>(a, nb, kper, st) : launch_step_sp<FLUX_HLL, false, T>(a, nb, kper, st);
+      return gen ? launch_step_sp<FLUX_LXF, true, T>(a, nb, kper, st) : launch_step_sp<FLUX_LXF, false, T>(a, nb, kper, st);
+    }
+  }
   if (flux == HS_FLUX_HLL) return gen ? launch_step_t<MODEL, FLUX_HLL, true, T>(a, nb, st) : launch_step_t<MODEL, FLUX_HLL, false, T>(a, nb, st);
   return gen ? launch_step_t<MODEL, FLUX_LXF, true, T>(a, nb, st) : launch_step_t<MODEL, FLUX_LXF, false, T>(a, nb, st);
 }
@@ -398,6 +442,7 @@ static int read_status(hs_ctx* c) {
     bad |= st;
   }
   if (bad & 2) return fail(HS_ERR_CUDA, "peer-memory exchange timed out: a device of the context stopped stepping");
+  if (bad & 4) return fail(HS_ERR_CUDA, "tile copy (TMA) did not complete: internal error of the single-phase step kernel");
   if (bad) return fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError");
   return HS_OK;
 }

@@ -512,6 +512,294 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_step_sp: the single-phase time step as a TMA-fed tile pipeline.
+//
+// Same arithmetic as k_step<MODEL_SP13> (same inline functions, same expressions), different data
+// movement.  In k_step a block spends a quarter of its life waiting for its own tile (4 blocks/SM at
+// 128 registers: nothing else to run), so here a block walks over `kper` tiles (grid-stride, so the
+// hardware block scheduler still balances the SMs -- a static persistent partition loses ~10 %,
+// profiles/r01_experiments.md) and, while it computes tile k, the TMA engine (cp.async.bulk, one
+// 1040-byte row copy per state / cache row, completion on an mbarrier) fills the other shared-memory
+// stage with tile k+1.  No register or instruction cost for the loads, no load latency on the
+// critical path after the first tile.
+//   * rows are copied from the 16-byte-aligned address at or below the tile start (130 doubles per
+//     row), so any ncells / stride parity works: slot j of cell `col` sits at column col + parity(row);
+//   * the physical flux of BOTH cells of a face comes straight from the cached 1/rho and stress rows
+//     (23 FP64 instructions) instead of a shared flux tile + barrier;
+//   * the face flux is handed to the left cell by a warp shuffle (shared memory only across the
+//     three warp boundaries), so nothing reads a stage after the one barrier of a tile and the
+//     stage can be refilled while the block is still in its update phase;
+//   * max(lambda) is kept per thread across the tiles of a problem: one atomicMax per block
+//     instead of one per tile.
+// Tiles whose 130-element window would run past the end of the arrays (the last one or two of the
+// launch) are loaded by the threads themselves.
+// ------------------------------------------------------------------------------------------------
+namespace tma {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.b32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+}  // namespace tma
+
+constexpr int SP_TS = 130;                       // doubles per stage row: 128 cells + alignment slack
+constexpr int SP_NST = 19;                       // rows per stage: 13 state rows (slots 2..14) + 6 cache rows
+constexpr unsigned SP_ROW_BYTES = SP_TS * 8, SP_STAGE_BYTES = SP_NST * SP_ROW_BYTES;
+// SP13 variable stored in record slot j (inverse of sp_slot)
+__host__ __device__ constexpr int sp_var(int j) { return j < 5 ? j - 2 : (j == 5 ? 12 : 3 + 3 * ((j - 6) % 3) + (j - 6) / 3); }
+template <int T> constexpr size_t step_sp_smem_bytes() {
+  return sizeof(double) * (2 * SP_NST * SP_TS + 2 * (T / 32) * 13 + T / 32 + 24 + 2);
+}
+
+template <int FLUX, bool GEN, int T>
+__global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, const int kper) {
+  static_assert(T == 128, "stage rows hold 128 cells");
+  extern __shared__ __align__(128) double smem[];
+  double* const stage0 = smem;                                   // [2][SP_NST][SP_TS]
+  double* const Hb = smem + 2 * SP_NST * SP_TS;                  // [2][T/32][13] face flux of lane 0 of every warp
+  double* const red = Hb + 2 * (T / 32) * 13;                    // [T/32]
+  double* const sc = red + T / 32;                               // [3][8]: dt, update factor, dx/dt, t, lambda_max
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(sc + 24);   // [2]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned ntiles = (unsigned)g.tiles_per_prob * (unsigned)g.nprob;
+  const EosDev& eos = g.eos.e[0];
+
+  auto write_scalars = [&](double* dst, unsigned long long lam_bits, double t) {
+    const double lam_cur = __longlong_as_double((long long)lam_bits);
+    const double dt0 = g.cfl * g.dx / lam_cur;           // main.jl:212
+    const double lambda0 = g.dx / dt0;                   // main.jl:223
+    dst[0] = dt0;
+    dst[1] = (FLUX == FLUX_HLL) ? dt0 / g.dx : 1.0 / lambda0;   // main.jl:225,59 / :40
+    dst[2] = lambda0;
+    dst[3] = t;
+    dst[4] = lam_cur;
+  };
+  // one row copy per lane of warp 0; the window starts at the even element at or below the tile start
+  auto issue = [&](long long off, double* st, uint64_t* bar) {
+    if (lane == 0) tma::mbar_arrive_expect_tx(bar, SP_STAGE_BYTES);
+    __syncwarp();
+    if (lane < SP_NST) {
+      const bool isq = lane < 13;
+      const int r = isq ? lane : lane - 13;
+      const int row = isq ? sp_slot(lane) - 2 : lane;
+      const long long e = (long long)r * g.stride + off;
+      const double* src = (isq ? g.Qin : g.aux_in) + (e - (e & 1));
+      tma::bulk_g2s(st + row * SP_TS, src, SP_ROW_BYTES, bar);
+    }
+  };
+
+  unsigned id = blockIdx.x;
+  int prob = (int)(id / (unsigned)g.tiles_per_prob), tile = (int)(id % (unsigned)g.tiles_per_prob);
+  long long off = (long long)prob * g.ncells + (long long)tile * (T - 2);
+  bool cur_tma = off + SP_TS <= g.stride;
+  if (tid == 0) {
+    tma::mbar_init(&mbar[0], 1);
+    tma::mbar_init(&mbar[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0 && cur_tma) issue(off, stage0, &mbar[0]);
+  if (tid == 0) write_scalars(sc, __ldg(g.lam + (size_t)g.cur * g.nprob + prob), __ldg(g.tt + (size_t)g.cur * g.nprob + prob));
+  __syncthreads();
+
+  unsigned phase_bits = 0;   // bit s: parity of the next completion of stage s
+  double lam_run = 0.0;
+  int bad = 0;
+  for (int k = 0; k < kper; ++k) {
+    const int s = k & 1;
+    double* const st = stage0 + s * (SP_NST * SP_TS);
+    const double* const scv = sc + (k % 3) * 8;
+    // ---- start fetching the next tile of this block ---------------------------------------------
+    const unsigned idn = id + gridDim.x;
+    const bool has_next = (k + 1 < kper) && idn < ntiles;
+    int probn = prob, tilen = 0;
+    long long offn = 0;
+    bool next_tma = false;
+    if (has_next) {
+      probn = (int)(idn / (unsigned)g.tiles_per_prob); tilen = (int)(idn % (unsigned)g.tiles_per_prob);
+      offn = (long long)probn * g.ncells + (long long)tilen * (T - 2);
+      next_tma = offn + SP_TS <= g.stride;
+    }
+    // (every thread passed the barrier of tile k-1, after which nobody reads stage s^1 any more)
+    if (warp == 0 && next_tma) issue(offn, stage0 + (s ^ 1) * (SP_NST * SP_TS), &mbar[s ^ 1]);
+    unsigned long long lam_n = 0ull;
+    double t_n = 0.0;
+    if (tid == 0 && has_next) {
+      lam_n = __ldg(g.lam + (size_t)g.cur * g.nprob + probn);
+      t_n = __ldg(g.tt + (size_t)g.cur * g.nprob + probn);
+    }
+
+    const int c = tile * (T - 2) + tid;
+    const bool valid = c < g.ncells;
+    const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
+    const int pe = (int)(off & 1), po = (int)((off + g.stride) & 1);
+    // slot j / cache row r of the cell in stage column `col`
+#define SQ(j, col) st[((j) - 2) * SP_TS + (col) + ((sp_var(j) & 1) ? po : pe)]
+#define SA(r, col) st[(13 + (r)) * SP_TS + (col) + (((r) & 1) ? po : pe)]
+    if (cur_tma) {
+      const unsigned par = (phase_bits >> s) & 1u;
+      unsigned spins = 0;
+      while (!tma::mbar_try_wait(&mbar[s], par)) {
+        if (++spins > (1u << 20)) { atomicOr(g.status, 4); break; }   // never hang the GPU on a lost copy
+      }
+      phase_bits ^= 1u << s;
+    } else {
+#pragma unroll
+      for (int v = 0; v < 13; ++v) SQ(sp_slot(v), tid) = __ldg(g.Qin + (size_t)v * g.stride + gi);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) SA(r, tid) = __ldg(g.aux_in + (size_t)r * g.stride + gi);
+      __syncthreads();
+    }
+
+    const bool own_interior = valid && tid >= 1 && tid <= T - 2 && c <= g.ncells - 2;
+    // frozen physical boundary cells, main.jl:219-220 (halo cells of a slab belong to the neighbour)
+    const bool own_frozen = valid && ((c == 0 && !(g.ghost & 1)) || (c == g.ncells - 1 && !(g.ghost & 2)));
+    const double dt = scv[0], upd = scv[1], lambda = scv[2], t_cur = scv[3];
+    const bool active = t_cur < g.t_end;                  // while t < T, main.jl:202
+    (void)lambda;
+
+    double q[15], F[15];   // own record and the numerical flux through the face left of it (slots 2..14)
+    double lamv = 0.0;
+    if (active) {
+      const int L = (tid >= 1) ? tid - 1 : tid;           // thread 0 evaluates a dummy face against itself
+      int fbad = 0;
+      double s_l = 0.0, s_r = 0.0, inv_ds = 0.0, k_q = 0.0;
+      if (FLUX == FLUX_HLL) {
+        // wave-speed bounds at Q_m = (Q_l + Q_r)/2, NumFluxes.jl:86-91
+        double m[3], A[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) m[i] = 0.5 * (SQ(2 + i, L) + SQ(2 + i, tid));
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A[i] = 0.5 * (SQ(6 + i, L) + SQ(6 + i, tid));
+        PhaseState sm;
+        phase_state<GEN, true>(eos, 1.0, m, 0.5 * (SQ(5, L) + SQ(5, tid)), A, sm);
+        fbad = sm.bad;
+        const double cm = phase_cmax(eos, sm);
+        const double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
+        s_l = fmin(0.0, fmin(lo_m, SA(0, L)));
+        s_r = fmax(0.0, fmax(hi_m, SA(1, tid)));
+        inv_ds = hs_rcp(s_r - s_l);
+        k_q = s_l * s_r * inv_ds;
+      }
+      // physical flux of both cells from their cached 1/rho and stress row (flux, Hyperelasticity.jl:99-114)
+      double ra[15], fa[15], fb[15];
+#pragma unroll
+      for (int j = 2; j < 15; ++j) { ra[j] = SQ(j, L); q[j] = SQ(j, tid); }
+      {
+        const double sl[3] = {SA(3, L), SA(4, L), SA(5, L)}, sr[3] = {SA(3, tid), SA(4, tid), SA(5, tid)};
+        sp_flux_cached(ra, SA(2, L), sl, fa);
+        sp_flux_cached(q, SA(2, tid), sr, fb);
+      }
+#pragma unroll
+      for (int j = 2; j < 15; ++j) {
+        const double Fa = flux_is_zero(j) ? 0.0 : fa[j], Fb = flux_is_zero(j) ? 0.0 : fb[j];
+        if (FLUX == FLUX_HLL) F[j] = (s_r * Fa - s_l * Fb) * inv_ds + k_q * (q[j] - ra[j]);   // NumFluxes.jl:78
+        else F[j] = 0.5 * (Fa + Fb) - 0.5 * lambda * (q[j] - ra[j]);                          // NumFluxes.jl:30
+      }
+      if (valid && tid >= 1) bad |= fbad;
+      if (lane == 0 && warp > 0) {
+#pragma unroll
+        for (int j = 2; j < 15; ++j) Hb[((k & 1) * (T / 32) + warp) * 13 + (j - 2)] = F[j];
+      }
+      if (own_frozen) {
+#pragma unroll
+        for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = q[sp_slot(v)];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) g.aux_out[(size_t)r * g.stride + gi] = SA(r, tid);
+        lamv = fmax(fabs(SA(0, tid)), fabs(SA(1, tid)));
+      }
+    } else if (own_interior || own_frozen) {   // this problem already reached t_end: carry it through unchanged
+#pragma unroll
+      for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = SQ(sp_slot(v), tid);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) g.aux_out[(size_t)r * g.stride + gi] = SA(r, tid);
+    }
+    if (tid == 0) {
+      if (has_next) write_scalars(sc + ((k + 1) % 3) * 8, lam_n, t_n);
+      if (!active && tile == 0) {
+        g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur;
+        g.lam[(size_t)g.nxt * g.nprob + prob] = (unsigned long long)__double_as_longlong(scv[4]);
+        g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
+      }
+    }
+#undef SQ
+#undef SA
+    __syncthreads();   // the only barrier of a tile: boundary fluxes visible, stage s free for the copy after next
+
+    if (active) {
+      // ---- conservative update (update_cell, main.jl:59 / :40) + wave bounds of the new state ----
+      double qn[15];
+#pragma unroll
+      for (int j = 2; j < 15; ++j) {
+        double Fr = __shfl_down_sync(FULL, F[j], 1);
+        if (lane == 31 && warp < T / 32 - 1) Fr = Hb[((k & 1) * (T / 32) + warp + 1) * 13 + (j - 2)];
+        qn[j] = own_interior ? q[j] - upd * (Fr + (-F[j])) : q[j];
+      }
+      if (own_interior) {
+#pragma unroll
+        for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = qn[sp_slot(v)];
+      }
+      // CFL sweep of the next step (get_eigvals, main.jl:204-211) on the state just produced
+      PhaseState sn;
+      phase_state<GEN, true>(eos, 1.0, qn + 2, qn[5], qn + 6, sn);
+      const double cn = phase_cmax(eos, sn);
+      const double lo_n = sn.u[0] - cn, hi_n = sn.u[0] + cn;
+      if (own_interior) {
+        bad |= sn.bad;
+        g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n;
+        g.aux_out[(size_t)2 * g.stride + gi] = sn.inv_den;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) g.aux_out[(size_t)(3 + r) * g.stride + gi] = sn.sig1[r];
+        lamv = fmax(fabs(lo_n), fabs(hi_n));
+      }
+      lam_run = fmax(lam_run, lamv);
+      if (tile == 0 && tid == 0) {
+        g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur + dt;   // main.jl:214
+        g.steps[prob] += 1;                                   // main.jl:215
+        if (g.dt_hist && g.hist_k < g.hist_cap) g.dt_hist[(size_t)prob * g.hist_cap + g.hist_k] = dt;
+        g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
+      }
+    }
+    // ---- max(lambda) of this block's share of the problem: one atomic when the problem changes ----
+    if (!has_next || probn != prob) {
+      lam_run = warp_max_nonneg(lam_run);
+      if (lane == 0) red[warp] = lam_run;
+      bad = __any_sync(FULL, bad);
+      if (bad && lane == 0) atomicOr(g.status, 1);
+      __syncthreads();
+      if (tid == 0 && active) {
+        double mx = red[0];
+#pragma unroll
+        for (int w = 1; w < T / 32; ++w) mx = fmax(mx, red[w]);
+        atomicMax(g.lam + (size_t)g.nxt * g.nprob + prob, (unsigned long long)__double_as_longlong(mx));
+      }
+      lam_run = 0.0;
+      bad = 0;
+    }
+    if (!has_next) break;
+    id = idn; prob = probn; tile = tilen; off = offn; cur_tma = next_tma;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CFL sweep on a resident state (main.jl:204-212): lo/hi per cell, lambda_max per problem, and
 // optionally the full get_eigvals output (6 per phase) in Julia layout (6*NPH, ncells*nprob).
 // ------------------------------------------------------------------------------------------------

@@ -124,6 +124,8 @@ class _Base:
         st = int(self._status.cpu()[0])
         if st & 2:
             raise L.HyperelasticError(L.HS_ERR_CUDA, "peer-memory exchange timed out: another rank stopped stepping")
+        if st & 4:
+            raise L.HyperelasticError(L.HS_ERR_CUDA, "tile copy (TMA) did not complete: internal error of the single-phase step kernel")
         if st != 0:
             raise L.DomainError(L.HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError")
 
