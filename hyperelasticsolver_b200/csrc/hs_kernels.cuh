@@ -592,14 +592,17 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     dst[3] = t;
     dst[4] = lam_cur;
   };
-  // one row copy per lane of warp 0; the window starts at the even element at or below the tile start
+  // 19 row copies per tile, spread over the four warps (a bulk copy is a uniform-datapath instruction: the lanes of a
+  // warp issue theirs one after the other, so one warp doing all 19 would reach the tile's barrier ~15 % late); the
+  // window starts at the even element at or below the tile start.  Copies of the other warps may complete before thread
+  // 0 has posted the expected byte count: the phase cannot complete before that arrival, and tx-count is signed.
   auto issue = [&](long long off, double* st, uint64_t* bar) {
-    if (lane == 0) tma::mbar_arrive_expect_tx(bar, SP_STAGE_BYTES);
-    __syncwarp();
-    if (lane < SP_NST) {
-      const bool isq = lane < 13;
-      const int r = isq ? lane : lane - 13;
-      const int row = isq ? sp_slot(lane) - 2 : lane;
+    if (tid == 0) tma::mbar_arrive_expect_tx(bar, SP_STAGE_BYTES);
+    const int rr = lane * (T / 32) + warp;
+    if (lane < (SP_NST + T / 32 - 1) / (T / 32) && rr < SP_NST) {
+      const bool isq = rr < 13;
+      const int r = isq ? rr : rr - 13;
+      const int row = isq ? sp_slot(rr) - 2 : rr;
       const long long e = (long long)r * g.stride + off;
       const double* src = (isq ? g.Qin : g.aux_in) + (e - (e & 1));
       tma::bulk_g2s(st + row * SP_TS, src, SP_ROW_BYTES, bar);
@@ -616,17 +619,19 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     tma::fence_mbar_init();
   }
   __syncthreads();
-  if (warp == 0 && cur_tma) issue(off, stage0, &mbar[0]);
-  if (tid == 0) write_scalars(sc, __ldg(g.lam + (size_t)g.cur * g.nprob + prob), __ldg(g.tt + (size_t)g.cur * g.nprob + prob));
+  if (cur_tma) issue(off, stage0, &mbar[0]);
+  // the per-problem scalars (three IEEE divisions) are the job of one thread of warp 1, and only when the problem changes
+  if (tid == 32) write_scalars(sc, __ldg(g.lam + (size_t)g.cur * g.nprob + prob), __ldg(g.tt + (size_t)g.cur * g.nprob + prob));
   __syncthreads();
 
   unsigned phase_bits = 0;   // bit s: parity of the next completion of stage s
+  int sci = 0;               // scalar slot of the current problem
   double lam_run = 0.0;
   int bad = 0;
   for (int k = 0; k < kper; ++k) {
     const int s = k & 1;
     double* const st = stage0 + s * (SP_NST * SP_TS);
-    const double* const scv = sc + (k % 3) * 8;
+    const double* const scv = sc + sci * 8;
     // ---- start fetching the next tile of this block ---------------------------------------------
     const unsigned idn = id + gridDim.x;
     const bool has_next = (k + 1 < kper) && idn < ntiles;
@@ -639,10 +644,11 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       next_tma = offn + SP_TS <= g.stride;
     }
     // (every thread passed the barrier of tile k-1, after which nobody reads stage s^1 any more)
-    if (warp == 0 && next_tma) issue(offn, stage0 + (s ^ 1) * (SP_NST * SP_TS), &mbar[s ^ 1]);
+    if (next_tma) issue(offn, stage0 + (s ^ 1) * (SP_NST * SP_TS), &mbar[s ^ 1]);
+    const bool new_prob = has_next && probn != prob;
     unsigned long long lam_n = 0ull;
     double t_n = 0.0;
-    if (tid == 0 && has_next) {
+    if (tid == 32 && new_prob) {
       lam_n = __ldg(g.lam + (size_t)g.cur * g.nprob + probn);
       t_n = __ldg(g.tt + (size_t)g.cur * g.nprob + probn);
     }
@@ -732,8 +738,8 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 #pragma unroll
       for (int r = 0; r < 6; ++r) g.aux_out[(size_t)r * g.stride + gi] = SA(r, tid);
     }
+    if (tid == 32 && new_prob) write_scalars(sc + ((sci + 1) % 3) * 8, lam_n, t_n);
     if (tid == 0) {
-      if (has_next) write_scalars(sc + ((k + 1) % 3) * 8, lam_n, t_n);
       if (!active && tile == 0) {
         g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur;
         g.lam[(size_t)g.nxt * g.nprob + prob] = (unsigned long long)__double_as_longlong(scv[4]);
@@ -747,11 +753,12 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     if (active) {
       // ---- conservative update (update_cell, main.jl:59 / :40) + wave bounds of the new state ----
       double qn[15];
+      const double upd_own = own_interior ? upd : 0.0;   // halo / boundary cells keep their state: q - 0 * (finite) = q
 #pragma unroll
       for (int j = 2; j < 15; ++j) {
         double Fr = __shfl_down_sync(FULL, F[j], 1);
         if (lane == 31 && warp < T / 32 - 1) Fr = Hb[((k & 1) * (T / 32) + warp + 1) * 13 + (j - 2)];
-        qn[j] = own_interior ? q[j] - upd * (Fr + (-F[j])) : q[j];
+        qn[j] = q[j] - upd_own * (Fr + (-F[j]));
       }
       if (own_interior) {
 #pragma unroll
@@ -795,6 +802,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       bad = 0;
     }
     if (!has_next) break;
+    if (new_prob) sci = (sci + 1) % 3;
     id = idn; prob = probn; tile = tilen; off = offn; cur_tma = next_tma;
   }
 }
