@@ -208,9 +208,9 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
       for (int k = 0; k < 9; ++k) A[k] = 0.5 * (a[(6 + k) * T] + b[(6 + k) * T]);
       const double alpha = MPH ? 0.5 * (a[0] + b[0]) : 1.0;
       PhaseState sm;
-      phase_state<GEN, !MPH>(eos, alpha, m, 0.5 * (a[5 * T] + b[5 * T]), A, sm);
+      phase_state<GEN, !MPH, true>(eos, alpha, m, 0.5 * (a[5 * T] + b[5 * T]), A, sm);
       bad |= sm.bad;
-      const double cm = phase_cmax(eos, sm);
+      const double cm = phase_cmax<true>(eos, sm);
       double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
       if (MPH) {
         lo_m = fmin(lo_m, __shfl_xor_sync(FULL, lo_m, 1));
@@ -466,8 +466,8 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     }
     // CFL sweep of the next step (get_eigvals, main.jl:204-211) on the state just produced
     PhaseState sn;
-    phase_state<GEN, MODEL == MODEL_SP13>(eos, (MODEL == MODEL_MPH30) ? qn[0] : 1.0, qn + 2, qn[5], qn + 6, sn);
-    const double cn = phase_cmax(eos, sn);
+    phase_state<GEN, MODEL == MODEL_SP13, true>(eos, (MODEL == MODEL_MPH30) ? qn[0] : 1.0, qn + 2, qn[5], qn + 6, sn);
+    const double cn = phase_cmax<true>(eos, sn);
     double lo_n = sn.u[0] - cn, hi_n = sn.u[0] + cn;
     if (NPH == 2) {
       lo_n = fmin(lo_n, __shfl_xor_sync(FULL, lo_n, 1));
@@ -611,6 +611,8 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 
   unsigned id = blockIdx.x;
   int prob = (int)(id / (unsigned)g.tiles_per_prob), tile = (int)(id % (unsigned)g.tiles_per_prob);
+  // (problem, tile) of the next tile of this block follow by addition: one integer division pair per block, not per tile
+  const int step_q = (int)(gridDim.x / (unsigned)g.tiles_per_prob), step_r = (int)(gridDim.x % (unsigned)g.tiles_per_prob);
   long long off = (long long)prob * g.ncells + (long long)tile * (T - 2);
   bool cur_tma = off + SP_TS <= g.stride;
   if (tid == 0) {
@@ -639,7 +641,8 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     long long offn = 0;
     bool next_tma = false;
     if (has_next) {
-      probn = (int)(idn / (unsigned)g.tiles_per_prob); tilen = (int)(idn % (unsigned)g.tiles_per_prob);
+      probn = prob + step_q; tilen = tile + step_r;
+      if (tilen >= g.tiles_per_prob) { tilen -= g.tiles_per_prob; ++probn; }
       offn = (long long)probn * g.ncells + (long long)tilen * (T - 2);
       next_tma = offn + SP_TS <= g.stride;
     }
@@ -696,9 +699,9 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 #pragma unroll
         for (int i = 0; i < 9; ++i) A[i] = 0.5 * (SQ(6 + i, L) + SQ(6 + i, tid));
         PhaseState sm;
-        phase_state<GEN, true>(eos, 1.0, m, 0.5 * (SQ(5, L) + SQ(5, tid)), A, sm);
+        phase_state<GEN, true, true>(eos, 1.0, m, 0.5 * (SQ(5, L) + SQ(5, tid)), A, sm);
         fbad = sm.bad;
-        const double cm = phase_cmax(eos, sm);
+        const double cm = phase_cmax<true>(eos, sm);
         const double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
         s_l = fmin(0.0, fmin(lo_m, SA(0, L)));
         s_r = fmax(0.0, fmax(hi_m, SA(1, tid)));
@@ -766,8 +769,8 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       }
       // CFL sweep of the next step (get_eigvals, main.jl:204-211) on the state just produced
       PhaseState sn;
-      phase_state<GEN, true>(eos, 1.0, qn + 2, qn[5], qn + 6, sn);
-      const double cn = phase_cmax(eos, sn);
+      phase_state<GEN, true, true>(eos, 1.0, qn + 2, qn[5], qn + 6, sn);
+      const double cn = phase_cmax<true>(eos, sn);
       const double lo_n = sn.u[0] - cn, hi_n = sn.u[0] + cn;
       if (own_interior) {
         bad |= sn.bad;

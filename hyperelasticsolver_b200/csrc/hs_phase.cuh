@@ -61,18 +61,18 @@ inline EosDev make_eos_dev(const EosAbi& e) {
 inline bool eos_is_default_exponents(const EosAbi& e) { return e.alpha == 1.0 && e.beta == 3.0 && e.gamma == 2.0; }
 
 // Branch-free reciprocal / reciprocal square root / square root for the hot path: hardware seed
-// (MUFU.RCP64H / MUFU.RSQ64H, ~20 good bits) + two Newton steps in FMA form (20 -> 40 -> 80 bits,
-// i.e. <= 1-2 ulp).  The CUDA library versions are correctly rounded but carry a slow-path call with
-// register shuffling around every use; every argument here is an O(1) positive quantity of an
-// admissible state (inadmissible states are flagged separately through PhaseState::bad).
+// (MUFU.RCP64H / MUFU.RSQ64H read the high word only: ~20 good bits) + ONE third-order correction
+// (residual e ~ 1e-6 -> e^3 ~ 1e-18, i.e. <= 1-2 ulp after the final rounding; one FP64 instruction fewer
+// per reciprocal and three fewer per reciprocal square root than two Newton steps).  The CUDA library
+// versions are correctly rounded but carry a slow-path call with register shuffling around every use;
+// every argument here is an O(1) positive quantity of an admissible state (inadmissible states are
+// flagged separately through PhaseState::bad).
 HS_HD double hs_rcp(double x) {
 #ifdef __CUDA_ARCH__
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  return fma(y, e, y);
+  const double e = fma(-x, y, 1.0);          // 1 - x y
+  return fma(y, fma(e, e, e), y);            // y (1 + e + e^2)
 #else
   return 1.0 / x;
 #endif
@@ -81,10 +81,8 @@ HS_HD double hs_rsqrt(double x) {
 #ifdef __CUDA_ARCH__
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-(x * y), y, 1.0);      // 1 - x y^2
-  y = fma(0.5 * y, e, y);
-  e = fma(-(x * y), y, 1.0);
-  return fma(0.5 * y, e, y);
+  const double e = fma(-(x * y), y, 1.0);    // 1 - x y^2
+  return fma(y * e, fma(0.375, e, 0.5), y);  // y (1 + e/2 + 3 e^2/8)
 #else
   return 1.0 / sqrt(x);
 #endif
@@ -106,6 +104,7 @@ struct PhaseState {
   double alpha, inv_alpha, rho, den, inv_den;
   double u[3], Etot;
   double G[6], G2r1[3];   // Finger tensor, row 1 of G^2
+  double h22, h33;        // (G^2)_22, (G^2)_33 (only when phase_state is asked for them: WITH_H)
   double I1, J;           // tr G ;  I1^2/3 - I2
   double rB;              // (rho/rho0)^beta = I3^(beta/2)
   double th;              // cv t0 I3^(gamma/2) (S' - 1)
@@ -120,7 +119,9 @@ struct PhaseState {
 // ONE: alpha is the literal 1 (single-phase model) -- its reciprocal and powers fold away at compile time
 // (the reciprocal below is inline PTX, which the compiler cannot fold by itself; rcp(1) = 1 exactly, so
 // the result is bit-identical).
-template <bool GEN, bool ONE = false>
+// WITH_H: the caller goes on to the acoustic tensor, which needs the diagonal of G^2 anyway: tr(G^2) is then their
+// sum instead of a separate contraction.
+template <bool GEN, bool ONE = false, bool WITH_H = false>
 HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double E, const double* A, PhaseState& s) {
   // cofactors of A:  inv(A) = C^T / det A
   const double C11 = A[4] * A[8] - A[7] * A[5], C12 = A[7] * A[2] - A[1] * A[8], C13 = A[1] * A[5] - A[4] * A[2];
@@ -148,9 +149,20 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   s.G[5] = k2 * (C31 * C31 + C32 * C32 + C33 * C33);
   const double* G = s.G;
   s.I1 = G[0] + G[3] + G[5];
-  const double trG2 = G[0] * G[0] + G[3] * G[3] + G[5] * G[5] + 2.0 * (G[1] * G[1] + G[2] * G[2] + G[4] * G[4]);
-  const double I2 = 0.5 * (s.I1 * s.I1 - trG2);
-  s.J = s.I1 * s.I1 * (1.0 / 3.0) - I2;
+  // J = I1^2/3 - I2 with I2 = (I1^2 - tr G^2)/2 (Strains.jl:49-50), i.e. J = tr(G^2)/2 - I1^2/6
+  s.G2r1[0] = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
+  s.G2r1[1] = G[0] * G[1] + G[1] * G[3] + G[2] * G[4];
+  s.G2r1[2] = G[0] * G[2] + G[1] * G[4] + G[2] * G[5];
+  double trG2;
+  if (WITH_H) {
+    s.h22 = G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
+    s.h33 = G[2] * G[2] + G[4] * G[4] + G[5] * G[5];
+    trG2 = s.G2r1[0] + s.h22 + s.h33;
+  } else {
+    s.h22 = s.h33 = 0.0;
+    trG2 = G[0] * G[0] + G[3] * G[3] + G[5] * G[5] + 2.0 * (G[1] * G[1] + G[2] * G[2] + G[4] * G[4]);
+  }
+  s.J = fma(0.5, trG2, -(s.I1 * s.I1) * (1.0 / 6.0));
   // powers of I3 = r^2
   const double r = rho * eos.inv_rho0;
   double rA, rB, rC, irC;
@@ -181,9 +193,6 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   s.e2 = -eos.hb * rB;
   s.E3 = eos.kA1 * s.uc1 + eos.hg * s.th + eos.hb * eos.hbeta * rB * s.J;
   s.a = e1 + s.e2 * s.I1;
-  s.G2r1[0] = G[0] * G[0] + G[1] * G[1] + G[2] * G[2];
-  s.G2r1[1] = G[0] * G[1] + G[1] * G[3] + G[2] * G[4];
-  s.G2r1[2] = G[0] * G[2] + G[1] * G[4] + G[2] * G[5];
   const double m2r = -2.0 * rho;
   s.sig1[0] = m2r * (s.a * G[0] - s.e2 * s.G2r1[0] + s.E3);
   s.sig1[1] = m2r * (s.a * G[1] - s.e2 * s.G2r1[1]);
@@ -291,9 +300,10 @@ HS_HD double sym3_max_abs_eig(const double* a) {
   const double ip = hs_rsqrt(p2);
   const double p = p2 * ip;
   const double detb = b0 * (b3 * b5 - a[4] * a[4]) - a[1] * (a[1] * b5 - a[4] * a[2]) + a[2] * (a[1] * a[4] - b3 * a[2]);
-  double r = 0.5 * detb * (ip * ip * ip);
-  r = fmin(1.0, fmax(-1.0, r));
-  if (r >= -0.875 && p <= 2.0 * q) {
+  // |r| <= 1 up to roundoff; a value a few ulp above 1 only moves the root a few ulp above 2, and anything outside
+  // [-0.875, 1 + 1e-7] (NaN, or the garbage r of a numerically isotropic tensor) takes the cold path: no clamp needed
+  const double r = 0.5 * detb * (ip * ip * ip);
+  if (r >= -0.875 && r <= 1.0000001 && p <= 2.0 * q) {
     double mu = 1.7464452327513027 + r * (0.32800957660022223 + r * (-0.1425897443947186 + r * 0.08116787571408166));
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -311,6 +321,7 @@ HS_HD double sym3_max_abs_eig(const double* a) {
 // With dF = e_j (x) row1(F):  d rho = -rho d_1j,  dG = -(g_j e_1^T + e_1 g_j^T),
 // dI1 = -2 G_1j, dI2 = I1 dI1 + 2 (G^2)_1j, dI3/I3 = -2 d_1j  (SURVEY.md A.5); only G, G^2 and
 // the scalar energy derivatives enter -- F itself drops out.
+template <bool WITH_H = false>
 HS_HD void phase_acoustic_sym(const EosDev& eos, const PhaseState& s, double* S6) {
   // Collecting the terms of -2 (dM^(j)_1i - d_1j M_1i) by tensor structure and symmetrising
   // (g1, h1 = first rows of G, G^2; b0^2 rB = -2 e2, e1 = -(2/3) e2 I1):
@@ -320,9 +331,9 @@ HS_HD void phase_acoustic_sym(const EosDev& eos, const PhaseState& s, double* S6
   //   dE3c = (k0/2alpha)(alpha/2)(2 rA - 1) rA + (gamma/2)^2 th + (b0^2/2)(beta/2)^2 rB J.
   const double* G = s.G;
   const double h11 = s.G2r1[0], h12 = s.G2r1[1], h13 = s.G2r1[2];
-  const double h22 = G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
+  const double h22 = WITH_H ? s.h22 : G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
   const double h23 = G[1] * G[2] + G[3] * G[4] + G[4] * G[5];
-  const double h33 = G[2] * G[2] + G[4] * G[4] + G[5] * G[5];
+  const double h33 = WITH_H ? s.h33 : G[2] * G[2] + G[4] * G[4] + G[5] * G[5];
   const double e1 = s.a - s.e2 * s.I1;
   const double cG = -2.0 * (s.e2 * G[0] - s.a);
   const double cH = -2.0 * s.e2;
@@ -372,9 +383,10 @@ HS_HD void phase_acoustic_sym_n(const EosDev& eos, const PhaseState& s, const do
 
 // c_max = sqrt(max_k |eig_k(Omega)|): the only thing any consumer of get_eigvals keeps
 // (main.jl:210, NumFluxes.jl:90-91 take min / max / max|.| of u1 +- c_k).
+template <bool WITH_H = false>
 HS_HD double phase_cmax(const EosDev& eos, const PhaseState& s) {
   double S6[6];
-  phase_acoustic_sym(eos, s, S6);
+  phase_acoustic_sym<WITH_H>(eos, s, S6);
   return hs_sqrt(sym3_max_abs_eig(S6));
 }
 
