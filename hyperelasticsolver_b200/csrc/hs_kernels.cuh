@@ -203,12 +203,12 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
     {
       double m[3], A[9];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) m[k] = 0.5 * (a[(2 + k) * T] + b[(2 + k) * T]);
+      for (int k = 0; k < 3; ++k) m[k] = a[(2 + k) * T] + b[(2 + k) * T];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) A[k] = 0.5 * (a[(6 + k) * T] + b[(6 + k) * T]);
+      for (int k = 0; k < 9; ++k) A[k] = a[(6 + k) * T] + b[(6 + k) * T];
       const double alpha = MPH ? 0.5 * (a[0] + b[0]) : 1.0;
-      PhaseState sm;
-      phase_state<GEN, !MPH, true>(eos, alpha, m, 0.5 * (a[5 * T] + b[5 * T]), A, sm);
+      PhaseState sm;   // (m, E, A are the sums: phase_state folds the halving in, exactly)
+      phase_state<GEN, !MPH, true, true>(eos, alpha, m, a[5 * T] + b[5 * T], A, sm);
       bad |= sm.bad;
       const double cm = phase_cmax<true>(eos, sm);
       double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
@@ -695,11 +695,11 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
         // wave-speed bounds at Q_m = (Q_l + Q_r)/2, NumFluxes.jl:86-91
         double m[3], A[9];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) m[i] = 0.5 * (SQ(2 + i, L) + SQ(2 + i, tid));
+        for (int i = 0; i < 3; ++i) m[i] = SQ(2 + i, L) + SQ(2 + i, tid);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) A[i] = 0.5 * (SQ(6 + i, L) + SQ(6 + i, tid));
-        PhaseState sm;
-        phase_state<GEN, true, true>(eos, 1.0, m, 0.5 * (SQ(5, L) + SQ(5, tid)), A, sm);
+        for (int i = 0; i < 9; ++i) A[i] = SQ(6 + i, L) + SQ(6 + i, tid);
+        PhaseState sm;   // state at the mean of the two records (the halving is folded into phase_state, exactly)
+        phase_state<GEN, true, true, true>(eos, 1.0, m, SQ(5, L) + SQ(5, tid), A, sm);
         fbad = sm.bad;
         const double cm = phase_cmax<true>(eos, sm);
         const double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;

@@ -121,7 +121,10 @@ struct PhaseState {
 // the result is bit-identical).
 // WITH_H: the caller goes on to the acoustic tensor, which needs the diagonal of G^2 anyway: tr(G^2) is then their
 // sum instead of a separate contraction.
-template <bool GEN, bool ONE = false, bool WITH_H = false>
+// TWICE: m, E, A hold TWICE the record (the sum of two records: the caller wants the state at their mean, NumFluxes.jl:86).
+// Scaling by a power of two is exact, so folding the 1/2 into three scalar factors (1/8 on det, 1/4 on kappa, 1/2 on
+// 1/den) gives bit-identical results to halving the 13 inputs first.
+template <bool GEN, bool ONE = false, bool WITH_H = false, bool TWICE = false>
 HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double E, const double* A, PhaseState& s) {
   // cofactors of A:  inv(A) = C^T / det A
   const double C11 = A[4] * A[8] - A[7] * A[5], C12 = A[7] * A[2] - A[1] * A[8], C13 = A[1] * A[5] - A[4] * A[2];
@@ -131,16 +134,17 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   const double detA = A[0] * C11 + A[3] * C12 + A[6] * C13;
   const double ia = ONE ? 1.0 : hs_rcp(alpha);
   if (ONE) alpha = 1.0;
-  const double x = detA * (ia * ia * ia) * eos.inv_rho0;      // det(A/alpha)/rho0 = rho^2
+  const double x = (TWICE ? 0.125 * detA : detA) * (ia * ia * ia) * eos.inv_rho0;      // det(A/alpha)/rho0 = rho^2
   s.bad = !(x > 0.0);
   const double rs = hs_rsqrt(x);                              // 1/rho
   const double rho = x * rs;
   s.alpha = alpha; s.inv_alpha = ia; s.rho = rho; s.den = alpha * rho; s.inv_den = ia * rs;
-  s.u[0] = m[0] * s.inv_den; s.u[1] = m[1] * s.inv_den; s.u[2] = m[2] * s.inv_den;
-  s.Etot = E * s.inv_den;
+  const double idm = TWICE ? 0.5 * s.inv_den : s.inv_den;
+  s.u[0] = m[0] * idm; s.u[1] = m[1] * idm; s.u[2] = m[2] * idm;
+  s.Etot = E * idm;
   const double e_int = s.Etot - 0.5 * (s.u[0] * s.u[0] + s.u[1] * s.u[1] + s.u[2] * s.u[2]);
   // G = (F F^T)^-1 = kappa^2 C C^T with kappa = den/det A = 1/(alpha^2 rho0 rho)
-  const double kap = rs * ia * ia * eos.inv_rho0, k2 = kap * kap;
+  const double kap = (TWICE ? 0.25 * rs : rs) * ia * ia * eos.inv_rho0, k2 = kap * kap;
   s.G[0] = k2 * (C11 * C11 + C12 * C12 + C13 * C13);
   s.G[1] = k2 * (C11 * C21 + C12 * C22 + C13 * C23);
   s.G[2] = k2 * (C11 * C31 + C12 * C32 + C13 * C33);
