@@ -96,22 +96,30 @@ int launch_step_t(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
 }
 
 // Single-phase TMA tile pipeline (k_step_sp): every block walks over `kper` tiles, grid-stride.
-template <int FLUX, bool GEN, int T>
-int launch_step_sp(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st) {
+template <int FLUX, bool GEN, int T, bool SINGLE>
+int launch_step_sp_s(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st) {
   static bool attr_set = false;   // (one device attribute per kernel instantiation; set on every device it is used on)
   constexpr size_t smem = step_sp_smem_bytes<T>();
   static int attr_dev_mask = 0;
   int dev = 0;
   CU(cudaGetDevice(&dev));
   if (!attr_set || !(attr_dev_mask & (1 << (dev & 31)))) {
-    CU(cudaFuncSetAttribute(k_step_sp<FLUX, GEN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_step_sp<FLUX, GEN, T, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true; attr_dev_mask |= 1 << (dev & 31);
   }
   const int64_t nblocks = (ntiles + kper - 1) / kper;
-  k_step_sp<FLUX, GEN, T><<<(unsigned)nblocks, T, smem, st>>>(a, kper);
+  k_step_sp<FLUX, GEN, T, SINGLE><<<(unsigned)nblocks, T, smem, st>>>(a, kper);
   g_launches++;
   CU(cudaGetLastError());
   return HS_OK;
+}
+
+template <int FLUX, bool GEN, int T>
+int launch_step_sp(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st) {
+  // one problem (every grid configuration): problem index, scalars and column parities are loop invariants
+  const char* e = std::getenv("HS_SP_SINGLE");
+  if (a.nprob == 1 && !(e && e[0] == '0')) return launch_step_sp_s<FLUX, GEN, T, true>(a, ntiles, kper, st);
+  return launch_step_sp_s<FLUX, GEN, T, false>(a, ntiles, kper, st);
 }
 
 // tiles per block of the pipeline: 8, fewer on grids too small to fill the GPU twice over; HS_SP_TILES=k forces k

@@ -568,7 +568,9 @@ template <int T> constexpr size_t step_sp_smem_bytes() {
   return sizeof(double) * (2 * SP_NST * SP_TS + 2 * (T / 32) * 13 + T / 32 + 24 + 2);
 }
 
-template <int FLUX, bool GEN, int T>
+// SINGLE: one problem (nprob == 1, every grid config): the problem index, the per-problem scalars, the column parities
+// and the 64-bit tile offsets are then loop invariants or 32-bit, and max(lambda) is flushed once per block.
+template <int FLUX, bool GEN, int T, bool SINGLE>
 __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, const int kper) {
   static_assert(T == 128, "stage rows hold 128 cells");
   extern __shared__ __align__(128) double smem[];
@@ -610,9 +612,10 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   };
 
   unsigned id = blockIdx.x;
-  int prob = (int)(id / (unsigned)g.tiles_per_prob), tile = (int)(id % (unsigned)g.tiles_per_prob);
+  int prob = SINGLE ? 0 : (int)(id / (unsigned)g.tiles_per_prob), tile = SINGLE ? (int)id : (int)(id % (unsigned)g.tiles_per_prob);
   // (problem, tile) of the next tile of this block follow by addition: one integer division pair per block, not per tile
-  const int step_q = (int)(gridDim.x / (unsigned)g.tiles_per_prob), step_r = (int)(gridDim.x % (unsigned)g.tiles_per_prob);
+  const int step_q = SINGLE ? 0 : (int)(gridDim.x / (unsigned)g.tiles_per_prob);
+  const int step_r = SINGLE ? 0 : (int)(gridDim.x % (unsigned)g.tiles_per_prob);
   long long off = (long long)prob * g.ncells + (long long)tile * (T - 2);
   bool cur_tma = off + SP_TS <= g.stride;
   if (tid == 0) {
@@ -633,7 +636,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   for (int k = 0; k < kper; ++k) {
     const int s = k & 1;
     double* const st = stage0 + s * (SP_NST * SP_TS);
-    const double* const scv = sc + sci * 8;
+    const double* const scv = sc + (SINGLE ? 0 : sci * 8);
     // ---- start fetching the next tile of this block ---------------------------------------------
     const unsigned idn = id + gridDim.x;
     const bool has_next = (k + 1 < kper) && idn < ntiles;
@@ -641,14 +644,19 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     long long offn = 0;
     bool next_tma = false;
     if (has_next) {
-      probn = prob + step_q; tilen = tile + step_r;
-      if (tilen >= g.tiles_per_prob) { tilen -= g.tiles_per_prob; ++probn; }
-      offn = (long long)probn * g.ncells + (long long)tilen * (T - 2);
+      if (SINGLE) {
+        tilen = (int)idn;
+        offn = (long long)(tilen * (T - 2));          // < ncells < 2^31
+      } else {
+        probn = prob + step_q; tilen = tile + step_r;
+        if (tilen >= g.tiles_per_prob) { tilen -= g.tiles_per_prob; ++probn; }
+        offn = (long long)probn * g.ncells + (long long)tilen * (T - 2);
+      }
       next_tma = offn + SP_TS <= g.stride;
     }
     // (every thread passed the barrier of tile k-1, after which nobody reads stage s^1 any more)
     if (next_tma) issue(offn, stage0 + (s ^ 1) * (SP_NST * SP_TS), &mbar[s ^ 1]);
-    const bool new_prob = has_next && probn != prob;
+    const bool new_prob = !SINGLE && has_next && probn != prob;
     unsigned long long lam_n = 0ull;
     double t_n = 0.0;
     if (tid == 32 && new_prob) {
@@ -659,7 +667,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     const int c = tile * (T - 2) + tid;
     const bool valid = c < g.ncells;
     const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
-    const int pe = (int)(off & 1), po = (int)((off + g.stride) & 1);
+    const int pe = SINGLE ? 0 : (int)(off & 1), po = SINGLE ? (int)(g.stride & 1) : (int)((off + g.stride) & 1);   // (tile starts are even)
     // slot j / cache row r of the cell in stage column `col`
 #define SQ(j, col) st[((j) - 2) * SP_TS + (col) + ((sp_var(j) & 1) ? po : pe)]
 #define SA(r, col) st[(13 + (r)) * SP_TS + (col) + (((r) & 1) ? po : pe)]
@@ -789,7 +797,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       }
     }
     // ---- max(lambda) of this block's share of the problem: one atomic when the problem changes ----
-    if (!has_next || probn != prob) {
+    if (!has_next || (!SINGLE && probn != prob)) {
       lam_run = warp_max_nonneg(lam_run);
       if (lane == 0) red[warp] = lam_run;
       bad = __any_sync(FULL, bad);
@@ -806,7 +814,9 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     }
     if (!has_next) break;
     if (new_prob) sci = (sci + 1) % 3;
-    id = idn; prob = probn; tile = tilen; off = offn; cur_tma = next_tma;
+    id = idn; tile = tilen; cur_tma = next_tma;
+    if (SINGLE) off = (long long)(tile * (T - 2));
+    else { prob = probn; off = offn; }
   }
 }
 

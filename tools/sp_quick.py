@@ -1,9 +1,11 @@
-"""Development aid: one-line timing of the single-phase pipeline at the default settings (HLL and LxF), 2^23 cells."""
-import sys, os, time, json
+"""Development aid: one-line timings of the single-phase pipeline (HLL and LxF), 2^23 cells; extra arguments KEY=VALUE
+are environment settings to compare against the default (e.g. HS_SP_SINGLE=0 HS_SP_TILES=4)."""
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import hyperelasticsolver_b200 as H
 from tools.sp_pipeline_bench import run
 if __name__ == "__main__":
-    logn = int(sys.argv[1]) if len(sys.argv) > 1 else 23
-    for flux in ("hll", "lxf"):
-        run(logn, 20, flux, {})
+    envs = [{}] + [dict([a.split("=", 1)]) for a in sys.argv[1:]]
+    for _ in range(2):
+        for env in envs:
+            run(23, 20, "hll", env)
+    run(23, 20, "lxf", {})
