@@ -44,7 +44,12 @@ struct EosDev {
   double b0sq, hb;        // b0^2, b0^2/2
   double kA, kA1;         // k0/(2 alpha^2), k0/(2 alpha)
   double ea, eb, eg;      // alpha, beta, gamma
-  double ha, hbeta, hg;   // alpha/2, beta/2, gamma/2
+  double hbeta, hg;       // beta/2, gamma/2
+  // products the closed forms use as they stand (one FP64 instruction each time they would be formed in a kernel)
+  double kA1ha;           // (k0/2alpha)(alpha/2)
+  double c_a;             // -b0^2/6:      a = e1 + e2 I1 = c_a rB I1   (e1 = b0^2 rB I1/3, e2 = -b0^2 rB/2, so e1 = -2a)
+  double c_kg;            // 2 (1 + beta): kg = c_kg a,  kh = -c_kg e2  (phase_acoustic_sym)
+  double hg2, hb2;        // (gamma/2)^2, (beta/2)^2
 };
 
 inline EosDev make_eos_dev(const EosAbi& e) {
@@ -55,7 +60,11 @@ inline EosDev make_eos_dev(const EosAbi& e) {
   d.b0sq = e.b0sq; d.hb = 0.5 * e.b0sq;
   d.kA = 0.5 * e.k0 / (e.alpha * e.alpha); d.kA1 = 0.5 * e.k0 / e.alpha;
   d.ea = e.alpha; d.eb = e.beta; d.eg = e.gamma;
-  d.ha = 0.5 * e.alpha; d.hbeta = 0.5 * e.beta; d.hg = 0.5 * e.gamma;
+  d.hbeta = 0.5 * e.beta; d.hg = 0.5 * e.gamma;
+  d.kA1ha = d.kA1 * (0.5 * e.alpha);
+  d.c_a = -e.b0sq / 6.0;
+  d.c_kg = 2.0 * (1.0 + e.beta);
+  d.hg2 = d.hg * d.hg; d.hb2 = d.hbeta * d.hbeta;
   return d;
 }
 inline bool eos_is_default_exponents(const EosAbi& e) { return e.alpha == 1.0 && e.beta == 3.0 && e.gamma == 2.0; }
@@ -107,6 +116,7 @@ struct PhaseState {
   double h22, h33;        // (G^2)_22, (G^2)_33 (only when phase_state is asked for them: WITH_H)
   double I1, J;           // tr G ;  I1^2/3 - I2
   double rB;              // (rho/rho0)^beta = I3^(beta/2)
+  double W;               // shear energy (b0^2/2) I3^(beta/2) J
   double th;              // cv t0 I3^(gamma/2) (S' - 1)
   double uc1, uc2;        // (rA-1) rA ;  (2 rA - 1) rA     (cold-compression pieces)
   double Sp;              // S' = exp(S/cv), clamped at 1e-6 (EquationsOfState.jl:152-154)
@@ -186,17 +196,18 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   const double am1 = rA - 1.0;
   s.uc1 = am1 * rA; s.uc2 = (2.0 * rA - 1.0) * rA;
   const double W = eos.hb * rB * s.J;
+  s.W = W;
   double Sp = (e_int - W - eos.kA * am1 * am1) * eos.inv_cvt0 * irC + 1.0;
   if (Sp != Sp) s.bad = 1;
   if (Sp < 1e-6) Sp = 1e-6;
   s.Sp = Sp;
   s.th = eos.cvt0 * rC * (Sp - 1.0);
   s.T = eos.t0 * rC * Sp;
-  // first derivatives of e(I1,I2,I3;S):  e1 = b0^2 rB I1/3, e2 = -b0^2 rB/2, E3 = e3*I3
-  const double e1 = eos.b0sq * rB * s.I1 * (1.0 / 3.0);
+  // first derivatives of e(I1,I2,I3;S):  e1 = b0^2 rB I1/3, e2 = -b0^2 rB/2, E3 = e3*I3 (its shear part is (beta/2) W);
+  // a = e1 + e2 I1 = -(b0^2/6) rB I1
   s.e2 = -eos.hb * rB;
-  s.E3 = eos.kA1 * s.uc1 + eos.hg * s.th + eos.hb * eos.hbeta * rB * s.J;
-  s.a = e1 + s.e2 * s.I1;
+  s.E3 = eos.kA1 * s.uc1 + eos.hg * s.th + eos.hbeta * W;
+  s.a = eos.c_a * (rB * s.I1);
   const double m2r = -2.0 * rho;
   s.sig1[0] = m2r * (s.a * G[0] - s.e2 * s.G2r1[0] + s.E3);
   s.sig1[1] = m2r * (s.a * G[1] - s.e2 * s.G2r1[1]);
@@ -338,21 +349,25 @@ HS_HD void phase_acoustic_sym(const EosDev& eos, const PhaseState& s, double* S6
   const double h22 = WITH_H ? s.h22 : G[1] * G[1] + G[3] * G[3] + G[4] * G[4];
   const double h23 = G[1] * G[2] + G[3] * G[4] + G[4] * G[5];
   const double h33 = WITH_H ? s.h33 : G[2] * G[2] + G[4] * G[4] + G[5] * G[5];
-  const double e1 = s.a - s.e2 * s.I1;
+  // with e1 = -2a:  kg = 2 (1 + beta) a,  kh = -2 (1 + beta) e2;  the shear part of dE3c is (beta/2)^2 W
   const double cG = -2.0 * (s.e2 * G[0] - s.a);
   const double cH = -2.0 * s.e2;
   const double cg = cH * (1.0 / 3.0);
-  const double kg = -2.0 * (0.5 * eos.hbeta * e1 - s.a * (1.0 + eos.hbeta));
-  const double kh = cH * (1.0 + eos.eb);
-  const double dE3c = eos.kA1 * eos.ha * s.uc2 + eos.hg * eos.hg * s.th + eos.hb * eos.hbeta * eos.hbeta * s.rB * s.J;
+  const double kg = eos.c_kg * s.a;
+  const double kh = -eos.c_kg * s.e2;
+  const double dE3c = eos.kA1ha * s.uc2 + eos.hg2 * s.th + eos.hb2 * s.W;
   const double k11 = 2.0 * (2.0 * dE3c + s.E3);
-  const double g1 = G[0], g2 = G[1], g3 = G[2];
-  S6[0] = cG * G[0] + cH * h11 + cg * g1 * g1 + 2.0 * (kg * g1 + kh * h11) + k11;
-  S6[1] = cG * G[1] + cH * h12 + cg * g1 * g2 + (kg * g2 + kh * h12);
-  S6[2] = cG * G[2] + cH * h13 + cg * g1 * g3 + (kg * g3 + kh * h13);
-  S6[3] = cG * G[3] + cH * h22 + cg * g2 * g2;
-  S6[4] = cG * G[4] + cH * h23 + cg * g2 * g3;
-  S6[5] = cG * G[5] + cH * h33 + cg * g3 * g3;
+  // entries collected by G / G^2 component (g1 = row 1 of G):
+  //   S11 = G11 (cG + 2 kg + cg G11) + h11 (cH + 2 kh) + k11,   S1j = G1j (cG + kg + cg G11) + h1j (cH + kh)
+  const double t1 = fma(cg, G[0], cG + kg);
+  const double c3 = cH + kh;
+  S6[0] = fma(G[0], t1 + kg, fma(h11, fma(2.0, kh, cH), k11));
+  S6[1] = fma(G[1], t1, h12 * c3);
+  S6[2] = fma(G[2], t1, h13 * c3);
+  const double cg2 = cg * G[1], cg3 = cg * G[2];
+  S6[3] = fma(cG, G[3], fma(cH, h22, cg2 * G[1]));
+  S6[4] = fma(cG, G[4], fma(cH, h23, cg2 * G[2]));
+  S6[5] = fma(cG, G[5], fma(cH, h33, cg3 * G[2]));
 }
 
 // The same tensor for an arbitrary unit normal n (EquationsOfState.jl:223-246 takes n; the 1-D driver
@@ -371,11 +386,10 @@ HS_HD void phase_acoustic_sym_n(const EosDev& eos, const PhaseState& s, const do
     hn[i] = H[i][0] * n[0] + H[i][1] * n[1] + H[i][2] * n[2];
   }
   const double nGn = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
-  const double e1 = s.a - s.e2 * s.I1;
   const double cG = -2.0 * (s.e2 * nGn - s.a), cH = -2.0 * s.e2, cg = cH * (1.0 / 3.0);
-  const double kg = -2.0 * (0.5 * eos.hbeta * e1 - s.a * (1.0 + eos.hbeta));
-  const double kh = cH * (1.0 + eos.eb);
-  const double dE3c = eos.kA1 * eos.ha * s.uc2 + eos.hg * eos.hg * s.th + eos.hb * eos.hbeta * eos.hbeta * s.rB * s.J;
+  const double kg = eos.c_kg * s.a;
+  const double kh = -eos.c_kg * s.e2;
+  const double dE3c = eos.kA1ha * s.uc2 + eos.hg2 * s.th + eos.hb2 * s.W;
   const double k11 = 2.0 * (2.0 * dE3c + s.E3);
   const int ix[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
   for (int k = 0; k < 6; ++k) {
