@@ -252,9 +252,10 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
         emit(j, 0.0, k_m * br + dq, k_p * br - dq);
       }
     } else {
+      const double w_l = s_r * inv_ds, w_r = s_l * inv_ds;                             // weights of F_l and F_r
 #pragma unroll
       for (int j = J0; j < 15; ++j)                                                    // NumFluxes.jl:78 (one-phase form)
-        emit(j, (s_r * HS_FLUX(Fa, j) - s_l * HS_FLUX(Fb, j)) * inv_ds + k_q * (b[j * T] - a[j * T]), 0.0, 0.0);
+        emit(j, fma(w_l, HS_FLUX(Fa, j), fma(-w_r, HS_FLUX(Fb, j), k_q * (b[j * T] - a[j * T]))), 0.0, 0.0);
     }
   } else {
     double acc[15];
@@ -715,6 +716,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
         s_r = fmax(0.0, fmax(hi_m, SA(1, tid)));
         inv_ds = hs_rcp(s_r - s_l);
         k_q = s_l * s_r * inv_ds;
+        s_l *= inv_ds; s_r *= inv_ds;                     // weights of F_l and F_r in the HLL flux
       }
       // physical flux of both cells from their cached 1/rho and stress row (flux, Hyperelasticity.jl:99-114)
       double ra[15], fa[15], fb[15];
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 #pragma unroll
       for (int j = 2; j < 15; ++j) {
         const double Fa = flux_is_zero(j) ? 0.0 : fa[j], Fb = flux_is_zero(j) ? 0.0 : fb[j];
-        if (FLUX == FLUX_HLL) F[j] = (s_r * Fa - s_l * Fb) * inv_ds + k_q * (q[j] - ra[j]);   // NumFluxes.jl:78
+        if (FLUX == FLUX_HLL) F[j] = fma(s_r, Fa, fma(-s_l, Fb, k_q * (q[j] - ra[j])));      // NumFluxes.jl:78
         else F[j] = 0.5 * (Fa + Fb) - 0.5 * lambda * (q[j] - ra[j]);                          // NumFluxes.jl:30
       }
       if (valid && tid >= 1) bad |= fbad;
@@ -786,7 +788,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
         g.aux_out[(size_t)2 * g.stride + gi] = sn.inv_den;
 #pragma unroll
         for (int r = 0; r < 3; ++r) g.aux_out[(size_t)(3 + r) * g.stride + gi] = sn.sig1[r];
-        lamv = fmax(fabs(lo_n), fabs(hi_n));
+        lamv = fabs(sn.u[0]) + cn;                        // = max(|lo_n|, |hi_n|), bit for bit (rounding is monotone and odd)
       }
       lam_run = fmax(lam_run, lamv);
       if (tile == 0 && tid == 0) {

@@ -197,21 +197,27 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   s.uc1 = am1 * rA; s.uc2 = (2.0 * rA - 1.0) * rA;
   const double W = eos.hb * rB * s.J;
   s.W = W;
-  double Sp = (e_int - W - eos.kA * am1 * am1) * eos.inv_cvt0 * irC + 1.0;
-  if (Sp != Sp) s.bad = 1;
-  if (Sp < 1e-6) Sp = 1e-6;
-  s.Sp = Sp;
-  s.th = eos.cvt0 * rC * (Sp - 1.0);
-  s.T = eos.t0 * rC * Sp;
+  // Thermal energy th = cv t0 I3^(gamma/2) (S' - 1).  entropy (EquationsOfState.jl:139-156) forms
+  // S' = th_raw / (cv t0 I3^(gamma/2)) + 1 from th_raw = e - W - U_cold and clamps it at 1e-6; multiplying the clamp
+  // through by the positive cv t0 I3^(gamma/2) gives th = max(th_raw, (1e-6 - 1) cv t0 I3^(gamma/2)) without the
+  // round trip through S' (and without the cancellation in S' - 1).  S' itself is only formed where it is asked for
+  // (cons2prim's entropy output); the temperature de/dS = t0 I3^(gamma/2) S' = t0 (I3^(gamma/2) + th / (cv t0)).
+  const double th_raw = e_int - W - eos.kA * am1 * am1;
+  if (th_raw != th_raw) s.bad = 1;
+  const double cr = eos.cvt0 * rC;
+  const double th_min = cr * (1e-6 - 1.0);
+  s.th = th_raw < th_min ? th_min : th_raw;
+  s.T = eos.t0 * fma(s.th, eos.inv_cvt0, rC);
+  s.Sp = fma(s.th * eos.inv_cvt0, irC, 1.0);
   // first derivatives of e(I1,I2,I3;S):  e1 = b0^2 rB I1/3, e2 = -b0^2 rB/2, E3 = e3*I3 (its shear part is (beta/2) W);
   // a = e1 + e2 I1 = -(b0^2/6) rB I1
   s.e2 = -eos.hb * rB;
   s.E3 = eos.kA1 * s.uc1 + eos.hg * s.th + eos.hbeta * W;
   s.a = eos.c_a * (rB * s.I1);
-  const double m2r = -2.0 * rho;
-  s.sig1[0] = m2r * (s.a * G[0] - s.e2 * s.G2r1[0] + s.E3);
-  s.sig1[1] = m2r * (s.a * G[1] - s.e2 * s.G2r1[1]);
-  s.sig1[2] = m2r * (s.a * G[2] - s.e2 * s.G2r1[2]);
+  const double m2r = -2.0 * rho, am = m2r * s.a, em = m2r * s.e2;   // sigma = -2 rho (a G - e2 G^2 + E3 I)
+  s.sig1[0] = fma(am, G[0], fma(-em, s.G2r1[0], m2r * s.E3));
+  s.sig1[1] = fma(am, G[1], -em * s.G2r1[1]);
+  s.sig1[2] = fma(am, G[2], -em * s.G2r1[2]);
 }
 
 // Physical x-flux of one phase in the 15-slot MPh order [0, den u1, mom(3), energy, A-block(9)].
