@@ -148,14 +148,15 @@ __device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const d
   acc[0] += w * uI[0];
   acc[2] += wi * n0; acc[3] += wi * n1; acc[4] += wi * n2;
   acc[5] += wi * (n0 * uI[0] + n1 * uI[1] + n2 * uI[2]);
-  const double dv[3] = {uI[0] - st.u[0], uI[1] - st.u[1], uI[2] - st.u[2]};
+  // rho F_1j u_1 + rho (F^T (u_I - u))_j: the two A_1j terms combine, A_1j (u_1 + (u_I - u)_1) = A_1j u_I1
+  const double dv1 = uI[1] - st.u[1], dv2 = uI[2] - st.u[2];
   const double wia = w * st.inv_alpha;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const double t = wia * A[3 * j];
-    acc[6 + 3 * j] += t * st.u[0] + wia * (A[3 * j] * dv[0] + A[3 * j + 1] * dv[1] + A[3 * j + 2] * dv[2]);
-    acc[7 + 3 * j] += t * st.u[1];
-    acc[8 + 3 * j] += t * st.u[2];
+    acc[6 + 3 * j] = fma(wia, fma(A[3 * j], uI[0], fma(A[3 * j + 1], dv1, A[3 * j + 2] * dv2)), acc[6 + 3 * j]);
+    acc[7 + 3 * j] = fma(t, st.u[1], acc[7 + 3 * j]);
+    acc[8 + 3 * j] = fma(t, st.u[2], acc[8 + 3 * j]);
   }
 }
 

@@ -144,7 +144,8 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   const double detA = A[0] * C11 + A[3] * C12 + A[6] * C13;
   const double ia = ONE ? 1.0 : hs_rcp(alpha);
   if (ONE) alpha = 1.0;
-  const double x = (TWICE ? 0.125 * detA : detA) * (ia * ia * ia) * eos.inv_rho0;      // det(A/alpha)/rho0 = rho^2
+  const double ia2r = ia * ia * eos.inv_rho0;                                          // 1/(alpha^2 rho0)
+  const double x = (TWICE ? 0.125 * detA : detA) * (ia * ia2r);                        // det(A/alpha)/rho0 = rho^2
   s.bad = !(x > 0.0);
   const double rs = hs_rsqrt(x);                              // 1/rho
   const double rho = x * rs;
@@ -154,7 +155,7 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   s.Etot = E * idm;
   const double e_int = s.Etot - 0.5 * (s.u[0] * s.u[0] + s.u[1] * s.u[1] + s.u[2] * s.u[2]);
   // G = (F F^T)^-1 = kappa^2 C C^T with kappa = den/det A = 1/(alpha^2 rho0 rho)
-  const double kap = (TWICE ? 0.25 * rs : rs) * ia * ia * eos.inv_rho0, k2 = kap * kap;
+  const double kap = (TWICE ? 0.25 * rs : rs) * ia2r, k2 = kap * kap;
   s.G[0] = k2 * (C11 * C11 + C12 * C12 + C13 * C13);
   s.G[1] = k2 * (C11 * C21 + C12 * C22 + C13 * C23);
   s.G[2] = k2 * (C11 * C31 + C12 * C32 + C13 * C33);
