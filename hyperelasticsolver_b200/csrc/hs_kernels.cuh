@@ -559,6 +559,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
       : "memory");
   return ok != 0;
 }
+// shared-memory access through a 32-bit shared-window address (the compiler otherwise re-derives the window base for
+// every predicated access of the warp-boundary hand-off: 4 extra instructions per load, issued by every lane)
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 }  // namespace tma
 
 constexpr int SP_TS = 130;                       // doubles per stage row: 128 cells + alignment slack
@@ -631,6 +639,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   if (tid == 32) write_scalars(sc, __ldg(g.lam + (size_t)g.cur * g.nprob + prob), __ldg(g.tt + (size_t)g.cur * g.nprob + prob));
   __syncthreads();
 
+  const unsigned hb0 = tma::smem_u32(Hb) + (unsigned)warp * (13u * 8u);   // this warp's slot of the boundary-flux buffer
   unsigned phase_bits = 0;   // bit s: parity of the next completion of stage s
   int sci = 0;               // scalar slot of the current problem
   double lam_run = 0.0;
@@ -736,8 +745,9 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       }
       if (valid && tid >= 1) bad |= fbad;
       if (lane == 0 && warp > 0) {
+        const unsigned hw = hb0 + (unsigned)(k & 1) * ((T / 32) * 13u * 8u);
 #pragma unroll
-        for (int j = 2; j < 15; ++j) Hb[((k & 1) * (T / 32) + warp) * 13 + (j - 2)] = F[j];
+        for (int j = 2; j < 15; ++j) tma::sts_f64(hw + 8u * (j - 2), F[j]);
       }
       if (own_frozen) {
 #pragma unroll
@@ -768,10 +778,12 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       // ---- conservative update (update_cell, main.jl:59 / :40) + wave bounds of the new state ----
       double qn[15];
       const double upd_own = own_interior ? upd : 0.0;   // halo / boundary cells keep their state: q - 0 * (finite) = q
+      const bool edge = lane == 31 && warp < T / 32 - 1;  // the right neighbour sits in the next warp
+      const unsigned hr = hb0 + (unsigned)(k & 1) * ((T / 32) * 13u * 8u) + 13u * 8u;
 #pragma unroll
       for (int j = 2; j < 15; ++j) {
         double Fr = __shfl_down_sync(FULL, F[j], 1);
-        if (lane == 31 && warp < T / 32 - 1) Fr = Hb[((k & 1) * (T / 32) + warp + 1) * 13 + (j - 2)];
+        if (edge) Fr = tma::lds_f64(hr + 8u * (j - 2));
         qn[j] = q[j] - upd_own * (Fr + (-F[j]));
       }
       if (own_interior) {

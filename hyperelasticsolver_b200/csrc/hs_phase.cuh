@@ -34,6 +34,20 @@
 
 namespace hs {
 
+// FP64 literals whose low word is not zero cannot be immediates of a DFMA / DMUL: the compiler builds each of them in
+// a register pair with two moves at every use (it will not keep them live at 128 registers).  As constant-bank
+// operands they cost nothing.
+#ifdef __CUDACC__
+struct HotLits { double third, sixth, th_clamp, tiny, r_hi, r_lo, mu0, mu1, mu2, mu3; };
+__constant__ HotLits c_lit = {1.0 / 3.0, 1.0 / 6.0, 1e-6 - 1.0, 1e-280, 1.0000001, -0.875,
+                              1.7464452327513027, 0.32800957660022223, -0.1425897443947186, 0.08116787571408166};
+#endif
+#ifdef __CUDA_ARCH__
+#define HS_LIT(field, value) (c_lit.field)
+#else
+#define HS_LIT(field, value) (value)
+#endif
+
 // Barton2009 block exactly as the C ABI passes it (EquationsOfState.jl:71-85 field order) ...
 struct EosAbi {
   double rho0, c0, cv, t0, b0, alpha, beta, gamma, b0sq, k0;
@@ -177,7 +191,7 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
     s.h22 = s.h33 = 0.0;
     trG2 = G[0] * G[0] + G[3] * G[3] + G[5] * G[5] + 2.0 * (G[1] * G[1] + G[2] * G[2] + G[4] * G[4]);
   }
-  s.J = fma(0.5, trG2, -(s.I1 * s.I1) * (1.0 / 6.0));
+  s.J = fma(0.5, trG2, -(s.I1 * s.I1) * HS_LIT(sixth, 1.0 / 6.0));
   // powers of I3 = r^2
   const double r = rho * eos.inv_rho0;
   double rA, rB, rC, irC;
@@ -206,7 +220,7 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   const double th_raw = e_int - W - eos.kA * am1 * am1;
   if (th_raw != th_raw) s.bad = 1;
   const double cr = eos.cvt0 * rC;
-  const double th_min = cr * (1e-6 - 1.0);
+  const double th_min = cr * HS_LIT(th_clamp, 1e-6 - 1.0);
   s.th = th_raw < th_min ? th_min : th_raw;
   s.T = eos.t0 * fma(s.th, eos.inv_cvt0, rC);
   s.Sp = fma(s.th * eos.inv_cvt0, irC, 1.0);
@@ -314,19 +328,20 @@ HS_HD double hs_rcp_approx(double x) {
 // other case, and the neighbourhood of a degenerate largest pair (r -> -1, where every
 // characteristic-polynomial method loses sqrt(eps)), takes the out-of-line Jacobi solve.
 HS_HD double sym3_max_abs_eig(const double* a) {
-  const double q = (a[0] + a[3] + a[5]) * (1.0 / 3.0);
+  const double q = (a[0] + a[3] + a[5]) * HS_LIT(third, 1.0 / 3.0);
   const double p1 = a[1] * a[1] + a[2] * a[2] + a[4] * a[4];
   const double b0 = a[0] - q, b3 = a[3] - q, b5 = a[5] - q;
-  const double p2 = (b0 * b0 + b3 * b3 + b5 * b5 + 2.0 * p1) * (1.0 / 6.0);
-  if (!(p2 > 1e-280)) return fabs(q);   // isotropic tensor (also keeps the flush-to-zero reciprocal-sqrt seed away from denormals)
+  const double p2 = (b0 * b0 + b3 * b3 + b5 * b5 + 2.0 * p1) * HS_LIT(sixth, 1.0 / 6.0);
+  if (!(p2 > HS_LIT(tiny, 1e-280))) return fabs(q);   // isotropic tensor (also keeps the flush-to-zero reciprocal-sqrt seed away from denormals)
   const double ip = hs_rsqrt(p2);
   const double p = p2 * ip;
   const double detb = b0 * (b3 * b5 - a[4] * a[4]) - a[1] * (a[1] * b5 - a[4] * a[2]) + a[2] * (a[1] * a[4] - b3 * a[2]);
   // |r| <= 1 up to roundoff; a value a few ulp above 1 only moves the root a few ulp above 2, and anything outside
   // [-0.875, 1 + 1e-7] (NaN, or the garbage r of a numerically isotropic tensor) takes the cold path: no clamp needed
   const double r = 0.5 * detb * (ip * ip * ip);
-  if (r >= -0.875 && r <= 1.0000001 && p <= 2.0 * q) {
-    double mu = 1.7464452327513027 + r * (0.32800957660022223 + r * (-0.1425897443947186 + r * 0.08116787571408166));
+  if (r >= HS_LIT(r_lo, -0.875) && r <= HS_LIT(r_hi, 1.0000001) && p <= 2.0 * q) {
+    double mu = fma(r, fma(r, fma(r, HS_LIT(mu3, 0.08116787571408166), HS_LIT(mu2, -0.1425897443947186)), HS_LIT(mu1, 0.32800957660022223)),
+                    HS_LIT(mu0, 1.7464452327513027));
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const double m2 = mu * mu;
@@ -359,7 +374,7 @@ HS_HD void phase_acoustic_sym(const EosDev& eos, const PhaseState& s, double* S6
   // with e1 = -2a:  kg = 2 (1 + beta) a,  kh = -2 (1 + beta) e2;  the shear part of dE3c is (beta/2)^2 W
   const double cG = -2.0 * (s.e2 * G[0] - s.a);
   const double cH = -2.0 * s.e2;
-  const double cg = cH * (1.0 / 3.0);
+  const double cg = cH * HS_LIT(third, 1.0 / 3.0);
   const double kg = eos.c_kg * s.a;
   const double kh = -eos.c_kg * s.e2;
   const double dE3c = eos.kA1ha * s.uc2 + eos.hg2 * s.th + eos.hb2 * s.W;
