@@ -299,10 +299,12 @@ def run_ours(args):
             traffic = tj.get("dram_bytes_per_launch")
             fp64_pct = tj.get("fp64_pipe_pct_of_peak")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_step (fused flux + update + next-step wave bounds)", "kernel_ms": kernel_ms,
+                "kernel": ("k_step_sp (TMA-fed tile pipeline: fused flux + update + next-step wave bounds)" if model == "sp13"
+                           else "k_step (fused path-conservative flux + update + next-step wave bounds)"), "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_cell_update": 2 * nvar * 8, "cell_updates_per_launch": updated_local, "peak_source": peak_src,
                 "fp64_pipe_pct_ncu": fp64_pct, "fp64_issue_peak_dfma_per_s": 1.708e13,
-                "note": "the path is FP64-pipe bound, not HBM bound (DESIGN.md): see profiles/ for the measured DFMA peak and pipe utilisation"}
+                "note": ("single-phase: DRAM traffic (algorithmic 208 B + 96 B of cached per-cell rows per cell update) and FP64 issue are both near their limits (DESIGN.md)"
+                         if model == "sp13" else "two-phase: FP64-pipe bound, not HBM bound (DESIGN.md): see profiles/ for the measured DFMA peak and pipe utilisation")}
 
     # ---- end to end through the host-buffer API ------------------------------------------------
     # every step: H2D of the whole (pinned) host state, CFL sweep, fused step, D2H of the new state.

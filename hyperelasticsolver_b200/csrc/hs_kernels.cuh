@@ -621,11 +621,12 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     }
   };
 
-  unsigned id = blockIdx.x;
+  // One grid: block b takes tiles b, b + gridDim, ... (blocks resident at the same time work on neighbouring tiles).
+  // Ensembles: block b takes the kper consecutive tiles from b * kper, so that it changes problem (new scalars, one
+  // more barrier for the max(lambda) flush) at most every tiles_per_prob tiles instead of at every tile.
+  unsigned id = SINGLE ? blockIdx.x : blockIdx.x * (unsigned)kper;
+  const unsigned id_step = SINGLE ? gridDim.x : 1u;
   int prob = SINGLE ? 0 : (int)(id / (unsigned)g.tiles_per_prob), tile = SINGLE ? (int)id : (int)(id % (unsigned)g.tiles_per_prob);
-  // (problem, tile) of the next tile of this block follow by addition: one integer division pair per block, not per tile
-  const int step_q = SINGLE ? 0 : (int)(gridDim.x / (unsigned)g.tiles_per_prob);
-  const int step_r = SINGLE ? 0 : (int)(gridDim.x % (unsigned)g.tiles_per_prob);
   long long off = (long long)prob * g.ncells + (long long)tile * (T - 2);
   bool cur_tma = off + SP_TS <= g.stride;
   if (tid == 0) {
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     double* const st = stage0 + s * (SP_NST * SP_TS);
     const double* const scv = sc + (SINGLE ? 0 : sci * 8);
     // ---- start fetching the next tile of this block ---------------------------------------------
-    const unsigned idn = id + gridDim.x;
+    const unsigned idn = id + id_step;
     const bool has_next = (k + 1 < kper) && idn < ntiles;
     int probn = prob, tilen = 0;
     long long offn = 0;
@@ -659,8 +660,8 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
         tilen = (int)idn;
         offn = (long long)(tilen * (T - 2));          // < ncells < 2^31
       } else {
-        probn = prob + step_q; tilen = tile + step_r;
-        if (tilen >= g.tiles_per_prob) { tilen -= g.tiles_per_prob; ++probn; }
+        tilen = tile + 1;
+        if (tilen >= g.tiles_per_prob) { tilen = 0; ++probn; }
         offn = (long long)probn * g.ncells + (long long)tilen * (T - 2);
       }
       next_tma = offn + SP_TS <= g.stride;
