@@ -11,9 +11,9 @@ keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.avg.per_second',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 md = [f'# {rnd} (final state of the round) — ncu `--set full` capture of the fused step kernel `k_step`\n',
-      'Command (gpurun, 1 GPU): `ncu --set full --clock-control none --import-source on -k regex:k_step -s 2 -c 1 -o gpurun_out/prof_X python bench.py [--workload mph30_2p24] --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1`; read with `ncu -i … --page raw --csv` and `--page source --csv` (`tools/summarize_ncu.py`). Numbers under ncu are not bench values (cold cache, serialised); `bench.py` times the same kernel with CUDA events (`' + rnd + '_bench_*.json`). Launch list of the bench command: `' + rnd + '_launches_sp13_2p24_final.csv`.\n']
+      'Command (gpurun, 1 GPU): `ncu --set full --clock-control none --import-source on -k regex:k_step[_sp] -s 2 -c 1 -o gpurun_out/prof_X python bench.py [--workload mph30_2p24] --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1`; read with `ncu -i … --page raw --csv` and `--page source --csv` (`tools/summarize_ncu.py`). Numbers under ncu are not bench values (cold cache, serialised); `bench.py` times the same kernel with CUDA events (`' + rnd + '_bench_*.json`). Launch list of the bench command: `' + rnd + '_launches_sp13_2p24_final.csv`.\n']
 traffic, fp64, dramp = {}, {}, {}
-for w, title, cells, nvar in (('sp', 'k_step<SP13,HLL,T=128> on 2^24 cells (bench.py default workload sp13_2p24)', 16777216, 13),
+for w, title, cells, nvar in (('sp', 'k_step_sp<HLL,T=128,SINGLE> on 2^24 cells (bench.py default workload sp13_2p24)', 16777216, 13),
                               ('mph', 'k_step<MPH30,HLL,T=128,SAME> on 2^24 cells (workload mph30_2p24)', 16777216, 30)):
     raw = subprocess.run(['ncu', '-i', f'gpurun_out/prof_{w}_final.ncu-rep', '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines())); hdr, units, r = rows[0], rows[1], rows[2]
@@ -24,7 +24,7 @@ for w, title, cells, nvar in (('sp', 'k_step<SP13,HLL,T=128> on 2^24 cells (benc
             i = hdr.index(k); md.append(f'| `{k}` | {r[i]} {units[i]} |'); vals[k] = (float(r[i].replace(",", "")), units[i])
     sc = lambda k: vals[k][0] * (1e9 if vals[k][1] == 'Gbyte' else 1e6)
     traffic[w] = sc('dram__bytes_read.sum') + sc('dram__bytes_write.sum'); fp64[w] = vals['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'][0]
-    dur = vals['gpu__time_duration.sum'][0] * 1e-3
+    dur = vals['gpu__time_duration.sum'][0] * {'us': 1e-6, 'ms': 1e-3, 's': 1.0, 'ns': 1e-9}[vals['gpu__time_duration.sum'][1]]
     dramp[w] = 100 * traffic[w] / dur / 6.45e12
     src = subprocess.run(['ncu', '-i', f'gpurun_out/prof_{w}_final.ncu-rep', '--page', 'source', '--csv', '--kernel-name', 'regex:k_step'], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
@@ -48,14 +48,16 @@ for w, title, cells, nvar in (('sp', 'k_step<SP13,HLL,T=128> on 2^24 cells (benc
 md.append(f'''
 ## Reading
 
-* **Traffic.** SP: the launch moves ~304 B per cell-update = 208 B algorithmic (read + write the 13 conserved doubles) + 96 B of
-  cached per-cell rows (wave bounds `lo/hi`, `1/rho`, stress row 1 — read and written once each). These are not re-reads:
-  caching them removes the state recovery from the step's head (~20 % of the FP64 work). MPh: ~512 B = 480 B + 32 B (`lo/hi`).
-* **Bound.** FP64 pipe, not HBM: MPh runs `pipe_fp64` at {fp64['mph']:.0f} % with DRAM at {dramp['mph']:.0f} %; SP sits between the two roofs
-  (FP64 {fp64['sp']:.0f} %, DRAM {dramp['sp']:.0f} % of the measured copy peak) and is limited by the latency of its 16 warps/SM
-  (instruction-count cuts no longer move it, `{rnd}_experiments.md`). Measured DFMA issue peak: 17.08 T/s (`{rnd}_fp64_peak.jsonl`).
-* **Occupancy.** <= 128 registers/thread (`__launch_bounds__(128, 4)`) -> 4 blocks = 16 warps per SM; 5 blocks (96
-  registers, spills) measured slower for both models (`{rnd}_experiments.md`).
+* **Single-phase (`k_step_sp`, TMA-fed tile pipeline).** DRAM traffic per cell-update = 208 B algorithmic (read + write the 13
+  conserved doubles) + 96 B of cached per-cell rows (wave bounds `lo/hi`, `1/rho`, stress row 1 -- read and written once each; not
+  re-reads: they remove the state recovery from the head of the step). The launch runs DRAM at {dramp['sp']:.0f} % of the measured copy peak
+  (6.45 TB/s) and the FP64 pipe at {fp64['sp']:.0f} %; with every FP64 warp instruction holding its scheduler's issue port for two cycles
+  (16 FP64 lanes per SM sub-partition) the kernel's issue ports are ~90 % busy: both roofs are close. `long_scoreboard` (waiting for
+  global loads) is gone from the stall profile (22 % in the plain kernel, `r01_ncu_k_step_mid.md`): the next tile arrives by `UBLKCP`
+  bulk copies while the block computes.
+* **Two-phase (`k_step`).** FP64 pipe, not HBM: `pipe_fp64` {fp64['mph']:.0f} % with DRAM at {dramp['mph']:.0f} %. Measured DFMA issue peak: 17.08 T/s (`{rnd}_fp64_peak.jsonl`).
+* **Occupancy.** 128 registers/thread (`__launch_bounds__(128, 4)`) -> 4 blocks = 16 warps per SM; 5 blocks (96 registers, spills)
+  measured slower for both kernels (`{rnd}_experiments.md`).
 ''')
 open(f'profiles/{rnd}_ncu_k_step_final.md', 'w').write('\n'.join(md))
 json.dump({'sp13_2p24': {'dram_bytes_per_launch': traffic['sp'], 'fp64_pipe_pct_of_peak': round(fp64['sp'], 1), 'dram_pct_of_measured_copy_peak': round(dramp['sp'], 1), 'registers_per_thread': 128, 'warps_per_sm': 16, 'source': f'profiles/{rnd}_ncu_k_step_final.md'},
