@@ -95,20 +95,48 @@ int launch_step_t(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
   return launch_step_s<MODEL, FLUX, GEN, T, (MODEL == MODEL_SP13)>(a, nblocks, st);
 }
 
-// Single-phase TMA tile pipeline (k_step_sp): every block walks over `kper` tiles, grid-stride.
-template <int FLUX, bool GEN, int T, bool SINGLE>
-int launch_step_sp_s(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st) {
-  static bool attr_set = false;   // (one device attribute per kernel instantiation; set on every device it is used on)
+// Tensor maps for the 2-D tile copies of k_step_sp<TM2D>: a (rows x stride) row-major FP64 array, box = 128 columns x all rows.
+// cuTensorMapEncodeTiled is a pure host function of the driver; it is reached through the runtime's entry-point query so that
+// the library does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+bool make_tile_map(CUtensorMap* m, const double* base, long long stride, int rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)stride, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(double)};
+  const cuuint32_t box[2] = {128u, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Single-phase TMA tile pipeline (k_step_sp): every block walks over `kper` tiles.
+template <int FLUX, bool GEN, int T, bool SINGLE, bool TM2D>
+int launch_step_sp_s(const StepArgs& a, int64_t ntiles, int kper, const CUtensorMap& mq, const CUtensorMap& ma, cudaStream_t st) {
   constexpr size_t smem = step_sp_smem_bytes<T>();
-  static int attr_dev_mask = 0;
+  static int attr_dev_mask = 0;   // (the attribute is per device and per kernel instantiation)
   int dev = 0;
   CU(cudaGetDevice(&dev));
-  if (!attr_set || !(attr_dev_mask & (1 << (dev & 31)))) {
-    CU(cudaFuncSetAttribute(k_step_sp<FLUX, GEN, T, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true; attr_dev_mask |= 1 << (dev & 31);
+  if (!(attr_dev_mask & (1 << (dev & 31)))) {
+    CU(cudaFuncSetAttribute(k_step_sp<FLUX, GEN, T, SINGLE, TM2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev_mask |= 1 << (dev & 31);
   }
   const int64_t nblocks = (ntiles + kper - 1) / kper;
-  k_step_sp<FLUX, GEN, T, SINGLE><<<(unsigned)nblocks, T, smem, st>>>(a, kper);
+  k_step_sp<FLUX, GEN, T, SINGLE, TM2D><<<(unsigned)nblocks, T, smem, st>>>(a, kper, mq, ma);
   g_launches++;
   CU(cudaGetLastError());
   return HS_OK;
@@ -118,8 +146,19 @@ template <int FLUX, bool GEN, int T>
 int launch_step_sp(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st) {
   // one problem (every grid configuration): problem index, scalars and column parities are loop invariants
   const char* e = std::getenv("HS_SP_SINGLE");
-  if (a.nprob == 1 && !(e && e[0] == '0')) return launch_step_sp_s<FLUX, GEN, T, true>(a, ntiles, kper, st);
-  return launch_step_sp_s<FLUX, GEN, T, false>(a, ntiles, kper, st);
+  const bool single = a.nprob == 1 && !(e && e[0] == '0');
+  // tensor-map tile copies need a row pitch that is a multiple of 16 bytes and 32-bit column coordinates
+  const char* e2 = std::getenv("HS_SP_TMA2D");
+  CUtensorMap mq, ma;
+  std::memset(&mq, 0, sizeof mq); std::memset(&ma, 0, sizeof ma);
+  const bool tm2d = !(e2 && e2[0] == '0') && (a.stride % 2 == 0) && a.stride < 0x7fffffffLL &&
+                    make_tile_map(&mq, a.Qin, a.stride, 13) && make_tile_map(&ma, a.aux_in, a.stride, 6);
+  if (tm2d) {
+    if (single) return launch_step_sp_s<FLUX, GEN, T, true, true>(a, ntiles, kper, mq, ma, st);
+    return launch_step_sp_s<FLUX, GEN, T, false, true>(a, ntiles, kper, mq, ma, st);
+  }
+  if (single) return launch_step_sp_s<FLUX, GEN, T, true, false>(a, ntiles, kper, mq, ma, st);
+  return launch_step_sp_s<FLUX, GEN, T, false, false>(a, ntiles, kper, mq, ma, st);
 }
 
 // tiles per block of the pipeline: 8, fewer on grids too small to fill the GPU twice over; HS_SP_TILES=k forces k

@@ -14,6 +14,7 @@
 //      lambda_max that the NEXT step's dt = cfl dx / lambda_max needs.
 // Intermediate fields (primitives, stress, fluxes, Q_hll, fluctuations) never touch HBM.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -559,6 +560,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
       : "memory");
   return ok != 0;
 }
+// one 2-D tile of a row-major (rows x stride) array through a tensor map: box = 128 columns x all rows, any start column
+__device__ __forceinline__ void tensor2d_g2s(void* dst, const CUtensorMap* map, int col, int row, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(row), "r"(smem_u32(bar))
+               : "memory");
+}
 // shared-memory access through a 32-bit shared-window address (the compiler otherwise re-derives the window base for
 // every predicated access of the warp-boundary hand-off: 4 extra instructions per load, issued by every lane)
 __device__ __forceinline__ double lds_f64(unsigned addr) {
@@ -580,12 +588,19 @@ template <int T> constexpr size_t step_sp_smem_bytes() {
 
 // SINGLE: one problem (nprob == 1, every grid config): the problem index, the per-problem scalars, the column parities
 // and the 64-bit tile offsets are then loop invariants or 32-bit, and max(lambda) is flushed once per block.
-template <int FLUX, bool GEN, int T, bool SINGLE>
-__global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, const int kper) {
+// TM2D: the state and the cached rows of a tile arrive as TWO tensor-map copies (13 x 128 and 6 x 128 doubles, any start
+// column, out-of-range columns zero-filled) issued by one thread, instead of 19 row copies spread over 20 lanes: ~40 fewer
+// issue slots per warp and tile, no column parities, no thread-loaded last tile.  Needs an even stride (row pitch multiple of
+// 16 bytes) and a stride below 2^31; the host falls back to the row copies otherwise.
+template <int FLUX, bool GEN, int T, bool SINGLE, bool TM2D>
+__global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, const int kper, const __grid_constant__ CUtensorMap tmQ,
+                                                           const __grid_constant__ CUtensorMap tmA) {
   static_assert(T == 128, "stage rows hold 128 cells");
+  constexpr int TS = TM2D ? T : SP_TS;          // doubles per stage row
+  constexpr int STAGE = SP_NST * TS;            // doubles per stage
   extern __shared__ __align__(128) double smem[];
   double* const stage0 = smem;                                   // [2][SP_NST][SP_TS]
-  double* const Hb = smem + 2 * SP_NST * SP_TS;                  // [2][T/32][13] face flux of lane 0 of every warp
+  double* const Hb = smem + 2 * SP_NST * SP_TS;                  // [2][T/32][13] face flux of lane 0 of every warp (same place for both stage widths)
   double* const red = Hb + 2 * (T / 32) * 13;                    // [T/32]
   double* const sc = red + T / 32;                               // [3][8]: dt, update factor, dx/dt, t, lambda_max
   uint64_t* const mbar = reinterpret_cast<uint64_t*>(sc + 24);   // [2]
@@ -609,6 +624,14 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   // window starts at the even element at or below the tile start.  Copies of the other warps may complete before thread
   // 0 has posted the expected byte count: the phase cannot complete before that arrival, and tx-count is signed.
   auto issue = [&](long long off, double* st, uint64_t* bar) {
+    if (TM2D) {
+      if (tid == 0) {
+        tma::mbar_arrive_expect_tx(bar, (unsigned)(STAGE * sizeof(double)));
+        tma::tensor2d_g2s(st, &tmQ, (int)off, 0, bar);
+        tma::tensor2d_g2s(st + 13 * TS, &tmA, (int)off, 0, bar);
+      }
+      return;
+    }
     if (tid == 0) tma::mbar_arrive_expect_tx(bar, SP_STAGE_BYTES);
     const int rr = lane * (T / 32) + warp;
     if (lane < (SP_NST + T / 32 - 1) / (T / 32) && rr < SP_NST) {
@@ -628,7 +651,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   const unsigned id_step = SINGLE ? gridDim.x : 1u;
   int prob = SINGLE ? 0 : (int)(id / (unsigned)g.tiles_per_prob), tile = SINGLE ? (int)id : (int)(id % (unsigned)g.tiles_per_prob);
   long long off = (long long)prob * g.ncells + (long long)tile * (T - 2);
-  bool cur_tma = off + SP_TS <= g.stride;
+  bool cur_tma = TM2D || off + SP_TS <= g.stride;
   if (tid == 0) {
     tma::mbar_init(&mbar[0], 1);
     tma::mbar_init(&mbar[1], 1);
@@ -647,7 +670,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   int bad = 0;
   for (int k = 0; k < kper; ++k) {
     const int s = k & 1;
-    double* const st = stage0 + s * (SP_NST * SP_TS);
+    double* const st = stage0 + s * STAGE;
     const double* const scv = sc + (SINGLE ? 0 : sci * 8);
     // ---- start fetching the next tile of this block ---------------------------------------------
     const unsigned idn = id + id_step;
@@ -664,10 +687,10 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
         if (tilen >= g.tiles_per_prob) { tilen = 0; ++probn; }
         offn = (long long)probn * g.ncells + (long long)tilen * (T - 2);
       }
-      next_tma = offn + SP_TS <= g.stride;
+      next_tma = TM2D || offn + SP_TS <= g.stride;
     }
     // (every thread passed the barrier of tile k-1, after which nobody reads stage s^1 any more)
-    if (next_tma) issue(offn, stage0 + (s ^ 1) * (SP_NST * SP_TS), &mbar[s ^ 1]);
+    if (next_tma) issue(offn, stage0 + (s ^ 1) * STAGE, &mbar[s ^ 1]);
     const bool new_prob = !SINGLE && has_next && probn != prob;
     unsigned long long lam_n = 0ull;
     double t_n = 0.0;
@@ -681,8 +704,9 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
     const int pe = SINGLE ? 0 : (int)(off & 1), po = SINGLE ? (int)(g.stride & 1) : (int)((off + g.stride) & 1);   // (tile starts are even)
     // slot j / cache row r of the cell in stage column `col`
-#define SQ(j, col) st[((j) - 2) * SP_TS + (col) + ((sp_var(j) & 1) ? po : pe)]
-#define SA(r, col) st[(13 + (r)) * SP_TS + (col) + (((r) & 1) ? po : pe)]
+    // (row copies: stage row = slot - 2, column shifted by the row's parity; tensor-map copies: stage row = variable, no shift)
+#define SQ(j, col) st[(TM2D ? sp_var(j) : (j) - 2) * TS + (col) + (TM2D ? 0 : ((sp_var(j) & 1) ? po : pe))]
+#define SA(r, col) st[(13 + (r)) * TS + (col) + (TM2D ? 0 : (((r) & 1) ? po : pe))]
     if (cur_tma) {
       const unsigned par = (phase_bits >> s) & 1u;
       unsigned spins = 0;

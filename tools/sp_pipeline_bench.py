@@ -6,7 +6,7 @@ import numpy as np
 import hyperelasticsolver_b200 as H
 
 def run(logn, steps, flux, env):
-    for k in ("HS_SP_TMA", "HS_SP_TILES", "HS_SP_SINGLE"):
+    for k in ("HS_SP_TMA", "HS_SP_TILES", "HS_SP_SINGLE", "HS_SP_TMA2D"):
         os.environ.pop(k, None)
     os.environ.update(env)
     n = 1 << logn
