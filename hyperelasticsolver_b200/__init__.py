@@ -5,12 +5,13 @@ The Python layer mirrors the reference's Julia module API (same function names, 
 meaning and error behaviour) and is a thin ctypes binding: all arithmetic runs in
 libhyperelastic_b200.so on the GPU.  There is no CPU fallback.
 """
-from ._lib import (Barton2009, DomainError, HyperelasticError, HLL, LXF, MPH30, SP13, build, lib)
+from ._lib import (Barton2009, Hank2016, DomainError, HyperelasticError, HLL, LXF, MPH30, SP13, build, lib)
 from .hyperelasticity_mph import (cons2prim_mph, flux_mph, get_eigvals, initial_states, noncons_flux, prim2cons_mph)
 from .num_fluxes import hll, lxf
 from .solver import Solver, initial_condition, update_cell
 from . import hyperelasticity
+from . import equations_of_state
 
-__all__ = ["Barton2009", "DomainError", "HyperelasticError", "HLL", "LXF", "MPH30", "SP13", "build", "lib",
+__all__ = ["Barton2009", "Hank2016", "equations_of_state", "DomainError", "HyperelasticError", "HLL", "LXF", "MPH30", "SP13", "build", "lib",
            "cons2prim_mph", "flux_mph", "get_eigvals", "initial_states", "noncons_flux", "prim2cons_mph",
            "hll", "lxf", "Solver", "initial_condition", "update_cell", "hyperelasticity"]

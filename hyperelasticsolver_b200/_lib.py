@@ -44,6 +44,14 @@ class Barton2009(C.Structure):
         return tuple(getattr(self, n) for n, _ in self._fields_)
 
 
+class Hank2016(C.Structure):
+    """EquationsOfState.jl:305-319 (same field order, same defaults)."""
+    _fields_ = [(n, C.c_double) for n in ("rho0", "mu", "gamma", "pres_inf", "a")]
+
+    def __init__(self, rho0=2.7, mu=26e9, gamma=3.4, pres_inf=21.5e9, a=0.5):
+        super().__init__(float(rho0), float(mu), float(gamma), float(pres_inf), float(a))
+
+
 class HsdProblem(C.Structure):
     _fields_ = [("model", C.c_int), ("nphase", C.c_int), ("gen", C.c_int), ("reserved", C.c_int),
                 ("ncells", C.c_int64), ("nprob", C.c_int64), ("stride", C.c_int64),
@@ -78,6 +86,9 @@ SIGNATURES = {
     "hs_get_eigvals": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _vp, _i64, C.c_int]),
     "hs_hll": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "hs_lxf": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, C.c_double, _vp, _vp, _vp, _i64, C.c_int]),
+    "hs_hank2016_energy": (C.c_int, [C.POINTER(Hank2016), _vp, _vp, _vp, _vp, _i64, C.c_int]),
+    "hs_hank2016_pressure": (C.c_int, [C.POINTER(Hank2016), _vp, _vp, _vp, _vp, _i64, C.c_int]),
+    "hs_hank2016_stress": (C.c_int, [C.POINTER(Hank2016), _vp, _vp, _vp, _vp, _i64, C.c_int]),
     "hs_selftest_math": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_int]),
     "hs_selftest_eig": (C.c_int, [_vp, _vp, _i64, C.c_int]),
     "hsd_problem_init": (C.c_int, [C.POINTER(HsdProblem), C.c_int, _eosp, C.c_int, _i64, _i64]),

@@ -822,6 +822,47 @@ int hs_selftest_eig(const double* s6, double* lam_max_abs, int64_t n, int device
   return HS_OK;
 }
 
+}  // extern "C"
+namespace {
+// Hank2016 batches: scalars s0[n], s1[n] (s1 may be NULL for the stress: its pressure argument does not enter),
+// tensor (NT, n), result (NO, n)
+template <int OP>
+int hank_batch(const hs_hank2016_t* eos, const double* s0, const double* s1, const double* ten, double* out, int64_t n, int device) {
+  constexpr int NT = (OP == HANK_PRESSURE) ? 3 : 9, NO = (OP == HANK_STRESS) ? 9 : 1;
+  if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  if (n < 1) return fail(HS_ERR_ARG, "n < 1");
+  if (!eos || !s0 || !ten || !out || (OP != HANK_STRESS && !s1)) return fail(HS_ERR_ARG, "null array");
+  if (!(eos->rho0 > 0.0) || eos->gamma == 1.0) return fail(HS_ERR_ARG, "Hank2016 needs rho0 > 0 and gamma != 1");
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return fail(HS_ERR_CUDA, "cudaSetDevice failed");
+  DevBuf d0, d1, dt, dout, dst;
+  CU(d0.alloc(n)); CU(dt.alloc((size_t)NT * n)); CU(dout.alloc((size_t)NO * n)); CU(dst.alloc(1));
+  CU(cudaMemcpy(d0.p, s0, sizeof(double) * n, cudaMemcpyHostToDevice));
+  if (OP != HANK_STRESS) { CU(d1.alloc(n)); CU(cudaMemcpy(d1.p, s1, sizeof(double) * n, cudaMemcpyHostToDevice)); }
+  CU(cudaMemcpy(dt.p, ten, sizeof(double) * NT * n, cudaMemcpyHostToDevice));
+  CU(cudaMemset(dst.p, 0, sizeof(double)));
+  HankAbi e = {eos->rho0, eos->mu, eos->gamma, eos->pres_inf, eos->a};
+  int* st = reinterpret_cast<int*>(dst.p);
+  k_hank<OP><<<(unsigned)((n + 127) / 128), 128>>>(e, d0.p, d1.p, dt.p, dout.p, n, st);
+  g_launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dout.p, sizeof(double) * NO * n, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  CU(cudaMemcpy(&bad, st, sizeof(int), cudaMemcpyDeviceToHost));
+  return bad ? fail(HS_ERR_DOMAIN, "det G <= 0: Julia's fractional power would throw DomainError") : HS_OK;
+}
+}  // namespace
+extern "C" {
+int hs_hank2016_energy(const hs_hank2016_t* eos, const double* den, const double* pres, const double* G, double* e_int, int64_t n, int device) {
+  return hank_batch<HANK_ENERGY>(eos, den, pres, G, e_int, n, device);
+}
+int hs_hank2016_pressure(const hs_hank2016_t* eos, const double* den, const double* e_int, const double* inv3, double* pres, int64_t n, int device) {
+  return hank_batch<HANK_PRESSURE>(eos, den, e_int, inv3, pres, n, device);
+}
+int hs_hank2016_stress(const hs_hank2016_t* eos, const double* den, const double* pres, const double* distortion, double* sigma, int64_t n, int device) {
+  return hank_batch<HANK_STRESS>(eos, den, pres, distortion, sigma, n, device);
+}
+
 int hs_cons2prim(int model, const hs_barton2009_t* eos, int nphase, const double* Q, double* P, int64_t n, int device) {
   return cellop<OP_CONS2PRIM>(model, eos, nphase, Q, P, n, device);
 }

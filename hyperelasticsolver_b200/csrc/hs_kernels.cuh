@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "hs_phase.cuh"
+#include "hs_hank.cuh"
 
 namespace hs {
 
@@ -1078,6 +1079,41 @@ __device__ __forceinline__ double energy_of_F(const EosDev& eos, double S, const
   const double U = eos.kA * (rA - 1.0) * (rA - 1.0) + eos.cvt0 * rC * (exp(S / eos.cv) - 1.0);   // EquationsOfState.jl:129-132
   const double W = eos.hb * rB * (I1 * I1 * (1.0 / 3.0) - I2);                                     // :134
   return U + W;
+}
+
+// Hank2016 (EquationsOfState.jl:301-356) as stateless batches: one thread per item; the (NT, n) Julia-layout tensor
+// argument (NT = 9 entries of G / of the distortion, or 3 invariants) is staged through shared memory so that the
+// global loads and the stress stores are contiguous.
+enum { HANK_ENERGY = 0, HANK_PRESSURE = 1, HANK_STRESS = 2 };
+template <int OP>
+__global__ void __launch_bounds__(128) k_hank(const HankAbi eos, const double* __restrict__ s0, const double* __restrict__ s1,
+                                              const double* __restrict__ ten, double* __restrict__ out, long long n, int* status) {
+  constexpr int NT = (OP == HANK_PRESSURE) ? 3 : 9, NO = (OP == HANK_STRESS) ? 9 : 1;
+  __shared__ double sh[128 * 9];
+  const long long base = (long long)blockIdx.x * 128;
+  const int cnt = (int)((n - base) < 128 ? (n - base) : 128);
+  for (int k = threadIdx.x; k < cnt * NT; k += 128) sh[k] = ten[base * NT + k];
+  __syncthreads();
+  const int l = threadIdx.x;
+  const bool valid = l < cnt;
+  double x[9];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) x[k] = sh[(valid ? l : 0) * NT + k];
+  const double a0 = valid ? s0[base + l] : 1.0;
+  const double a1 = (valid && OP != HANK_STRESS) ? s1[base + l] : 0.0;   // the pressure argument of stress() does not enter
+  int bad = 0;
+  double y[9];
+  if (OP == HANK_ENERGY) y[0] = hank_energy(eos, a0, a1, x, &bad);
+  else if (OP == HANK_PRESSURE) y[0] = hank_pressure(eos, a0, a1, x, &bad);
+  else hank_stress(eos, a0, x, y, &bad);
+  __syncthreads();
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < NO; ++k) sh[l * NO + k] = y[k];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < cnt * NO; k += 128) out[base * NO + k] = sh[k];
+  if (valid && bad) atomicOr(status, 1);
 }
 
 template <int MODEL, bool GEN, int OP>

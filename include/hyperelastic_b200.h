@@ -125,6 +125,28 @@ int hs_hll(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, 
 int hs_lxf(int model, const hs_barton2009_t* eos, int nphase, const double* Ql, const double* Qr, double lambda,
            double* cons, double* dm, double* dp, int64_t n, int device);
 
+/* ------------------------------------------------------------------------------------------
+ * Hank2016 equation of state, EquationsOfState.jl:301-364.  Dead code in the
+ * reference (nothing calls it; `energy` and `stress` pass a 3x3 Matrix to the Vector-only `invariants` /
+ * `finger`, Strains.jl:26,46, and cannot run as written): built as the stateless batches the three
+ * functions spell out, a 3x3 tensor being its 9 column-major entries.  The law is parametrised by
+ * (density, pressure), not by entropy, so it does not plug into the step kernels (whose state carries S).
+ * ------------------------------------------------------------------------------------------ */
+/* struct Hank2016, EquationsOfState.jl:305-319 (same field order; defaults 2.7, 26e9, 3.4, 21.5e9, 0.5) */
+typedef struct hs_hank2016 {
+  double rho0, mu, gamma, pres_inf, a;
+} hs_hank2016_t;
+/* energy(eos::Hank2016, den, pres, G) :317-331: den[n], pres[n], G (9, n) -> e_int[n] */
+int hs_hank2016_energy(const hs_hank2016_t* eos, const double* den, const double* pres, const double* G, double* e_int,
+                       int64_t n, int device);
+/* pressure(eos::Hank2016, den, e_int, i) :333-346: inv3 (3, n) = invariants(G), Strains.jl:46-52 -> pres[n] */
+int hs_hank2016_pressure(const hs_hank2016_t* eos, const double* den, const double* e_int, const double* inv3, double* pres,
+                         int64_t n, int device);
+/* stress(eos::Hank2016, den, pressure, distortion) :348-356: distortion (9, n) -> sigma (9, n) = -2 den G de/dG with
+ * G = finger(inv(distortion)).  pres may be NULL: the hydrodynamic energy does not depend on G. */
+int hs_hank2016_stress(const hs_hank2016_t* eos, const double* den, const double* pres, const double* distortion, double* sigma,
+                       int64_t n, int device);
+
 /* Device self-test hooks used by tests/: the hot path's branch-free reciprocal / reciprocal square root /
  * square root (x > 0) and its largest-|eigenvalue| solve of symmetric 3x3 tensors s6 = [11,12,13,22,23,33] (6, n). */
 int hs_selftest_math(const double* x, double* rcp, double* rsq, double* sq, int64_t n, int device);

@@ -5,7 +5,7 @@
 # reference modules it replaces
 #     HyperelasticityMPh: prim2cons_mph, cons2prim_mph, flux_mph, noncons_flux, get_eigvals   (HyperelasticityMPh.jl:13)
 #     NumFluxes:          lxf, hll                                                             (NumFluxes.jl:15)
-#     EquationsOfState:   Barton2009                                                           (EquationsOfState.jl:71)
+#     EquationsOfState:   Barton2009, Hank2016, energy, pressure, stress (Hank2016 methods)        (EquationsOfState.jl:71,305,366)
 # with the same argument meaning (`eos::Tuple{Barton2009,Barton2009}`, `Vector{Float64}` states),
 # plus batched methods on `Matrix{Float64}(nvar, n)` and a device-resident `Solver` that replaces
 # the two `Threads.@threads` loops of main.jl:204-227 with one call per step.
@@ -16,7 +16,7 @@
 #
 module HyperelasticB200
 
-export Barton2009, prim2cons_mph, cons2prim_mph, flux_mph, noncons_flux, get_eigvals, lxf, hll,
+export Barton2009, Hank2016, energy, pressure, stress, prim2cons_mph, cons2prim_mph, flux_mph, noncons_flux, get_eigvals, lxf, hll,
        Solver, upload!, download!, step!, advance!, wave_speeds, destroy!
 
 const LIB = get(ENV, "HYPERELASTIC_B200_LIB", joinpath(@__DIR__, "..", "hyperelasticsolver_b200", "libhyperelastic_b200.so"))
@@ -34,6 +34,12 @@ struct Barton2009
   function Barton2009(; _rho0=8.93, _c0=4.6, _cv=3.9e-4, _t0=300, _b0=2.1, _alpha=1, _beta=3, _gamma=2)
     new(_rho0, _c0, _cv, _t0, _b0, _alpha, _beta, _gamma, _b0^2, _c0^2 - (4 / 3) * _b0^2)
   end
+end
+
+# EquationsOfState.jl:305-319 -- same fields and defaults, concretely typed (== hs_hank2016_t)
+struct Hank2016
+  rho0::Float64; mu::Float64; gamma::Float64; pres_inf::Float64; a::Float64
+  Hank2016(rho0=2.7, mu=26e9, gamma=3.4, pres_inf=21.5e9, a=0.5) = new(rho0, mu, gamma, pres_inf, a)
 end
 
 function check(rc::Cint)
@@ -142,6 +148,29 @@ function advance!(s::Solver, flux::Function, cfl, dx, T; t=0.0, step_num=0, max_
       (Ptr{Cvoid}, Cint, Float64, Float64, Float64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
       s.ctx, flux === hll ? HS_FLUX_HLL : HS_FLUX_LXF, cfl, dx, T, max_steps, tv, sv, C_NULL))
   return s.nprob == 1 ? (tv[1], sv[1]) : (tv, sv)
+end
+
+# --- Hank2016 (EquationsOfState.jl:317-356): scalar methods like the reference, batched over columns ------------
+# A 3x3 tensor is a 3x3 Matrix or its 9 column-major entries (the reference's own methods mix the two and
+# cannot run as written); batches are (9, n) / (3, n) matrices with den, pres, e_int as length-n vectors.
+_vecf(x) = x isa Real ? Float64[x] : Vector{Float64}(x)
+function energy(eos::Hank2016, den, pres, G::Array{Float64}; device::Integer=0)
+  d = _vecf(den); p = _vecf(pres); n = length(d); out = Vector{Float64}(undef, n); e = Ref(eos)
+  GC.@preserve d p G out e check(ccall((:hs_hank2016_energy, LIB), Cint,
+      (Ptr{Hank2016}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Cint), e, d, p, G, out, n, device))
+  return den isa Real ? out[1] : out
+end
+function pressure(eos::Hank2016, den, e_int, i::Array{Float64}; device::Integer=0)
+  d = _vecf(den); ei = _vecf(e_int); n = length(d); out = Vector{Float64}(undef, n); e = Ref(eos)
+  GC.@preserve d ei i out e check(ccall((:hs_hank2016_pressure, LIB), Cint,
+      (Ptr{Hank2016}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Cint), e, d, ei, i, out, n, device))
+  return den isa Real ? out[1] : out
+end
+function stress(eos::Hank2016, den, pressure, distortion::Array{Float64}; device::Integer=0)
+  d = _vecf(den); p = _vecf(pressure); n = length(d); out = similar(distortion); e = Ref(eos)
+  GC.@preserve d p distortion out e check(ccall((:hs_hank2016_stress, LIB), Cint,
+      (Ptr{Hank2016}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Cint), e, d, p, distortion, out, n, device))
+  return out
 end
 
 end # module HyperelasticB200

@@ -53,6 +53,9 @@ def lib():
         L.hso_entropy.argtypes = [_dp, C.c_double, _dp]; L.hso_entropy.restype = C.c_double
         L.hso_temperature.argtypes = [_dp, C.c_double, _dp]; L.hso_temperature.restype = C.c_double
         L.hso_finger.argtypes = [_dp, _dp]
+        L.hso_hank_energy.argtypes = [_dp, C.c_double, C.c_double, _dp, _dp]
+        L.hso_hank_pressure.argtypes = [_dp, C.c_double, C.c_double, _dp, _dp]
+        L.hso_hank_stress.argtypes = [_dp, C.c_double, C.c_double, _dp, _dp]
         L.hso_invariants.argtypes = [_dp, _dp]
         L.hso_stress.argtypes = [_dp, C.c_double, _dp, _dp]
         L.hso_acoustic.argtypes = [_dp, C.c_double, _dp, _dp, _dp]
@@ -141,6 +144,26 @@ def get_eigvals_n(eos, Q, n):
 def energy(eos1, S, G): return lib().hso_energy(_p(_f(eos1)), float(S), _p(_f(G)))
 def entropy(eos1, e, G): return lib().hso_entropy(_p(_f(eos1)), float(e), _p(_f(G)))
 def temperature(eos1, S, G): return lib().hso_temperature(_p(_f(eos1)), float(S), _p(_f(G)))
+
+
+def hank2016(rho0=2.7, mu=26e9, gamma=3.4, pres_inf=21.5e9, a=0.5):
+    """EquationsOfState.jl:312-319 -> the 5-double parameter block."""
+    return np.array([rho0, mu, gamma, pres_inf, a], dtype=np.float64)
+
+
+def hank_energy(eos, den, pres, G):
+    """EquationsOfState.jl:317-331; G: 9 column-major entries.  Returns (e_int, domain_error)."""
+    e = np.empty(1); st = lib().hso_hank_energy(_p(_f(eos)), float(den), float(pres), _p(_f(G)), _p(e)); return e[0], st
+
+
+def hank_pressure(eos, den, e_int, inv3):
+    """EquationsOfState.jl:333-346; inv3 = invariants(G)."""
+    e = np.empty(1); st = lib().hso_hank_pressure(_p(_f(eos)), float(den), float(e_int), _p(_f(inv3)), _p(e)); return e[0], st
+
+
+def hank_stress(eos, den, pres, A):
+    """EquationsOfState.jl:348-356; A (distortion) and the result: 9 column-major entries."""
+    s = np.empty(9); st = lib().hso_hank_stress(_p(_f(eos)), float(den), float(pres), _p(_f(A)), _p(s)); return s, st
 
 
 def finger(F):

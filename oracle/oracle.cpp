@@ -197,6 +197,51 @@ static void acoustic(const Eos& eos, double ent, const double* F, const double* 
     }
 }
 
+// ------------------------------------------------------------------------------------
+// EquationsOfState.jl -- Hank2016 (:301-364).  Dead code in the reference (never called; `energy` and
+// `stress` cannot run as written: they pass a 3x3 Matrix to the Vector-only `invariants` / `finger`,
+// Strains.jl:26,46).  Restated with a 3x3 tensor == its 9 column-major entries, which is the only reading the
+// arithmetic allows; `pressure` (:333-346) runs as written.  Parity unpinned like the rest.
+// ------------------------------------------------------------------------------------
+struct Hank { double rho0, mu, gamma, pres_inf, a; };
+
+// EquationsOfState.jl:326-328 == :341-343
+template <class S> static S hank_e_el(const Hank& eos, const S* i) {
+  S j1 = i[0] / d_pow(i[2], 1.0 / 3);
+  S j2 = (i[0] * i[0] - 2.0 * i[1]) / d_pow(i[2], 2.0 / 3);
+  return (eos.mu / (4 * eos.rho0)) * (((1 - 2 * eos.a) / 3) * (j1 * j1) + eos.a * j2 + 3 * (eos.a - 1));
+}
+// EquationsOfState.jl:317-331
+template <class S> static S hank_energy(const Hank& eos, double den, double pres, const S* G) {
+  S i[3];
+  invariants(G, i);
+  if (!(value_of(i[2]) > 0.0)) g_domain_error = 1;  // negative base, fractional exponent -> DomainError
+  S e_el = hank_e_el(eos, i);
+  double e_h = (pres + eos.gamma * eos.pres_inf) / (den * (eos.gamma - 1));
+  return e_el + e_h;
+}
+// EquationsOfState.jl:333-346
+static double hank_pressure(const Hank& eos, double den, double e_int, const double* i) {
+  if (!(i[2] > 0.0)) g_domain_error = 1;
+  double e_el = hank_e_el(eos, i);
+  double e_h = e_int - e_el;
+  return e_h * (eos.gamma - 1) * den - eos.gamma * eos.pres_inf;
+}
+// EquationsOfState.jl:348-356: G = finger(inv(distortion)); gradient of the energy over the 9 entries of G
+static void hank_stress(const Hank& eos, double den, double pres, const double* A, double* sig) {
+  double Ai[9], G[9];
+  inv_(A, Ai);        // LinearAlgebra.inv: the inverse is unique, cofactor form used here
+  finger(Ai, G);
+  typedef Dual<double, 9> D9;
+  D9 Gd[9];
+  for (int i = 0; i < 9; ++i) { Gd[i] = D9(G[i]); Gd[i].d[i] = 1.0; }
+  D9 e = hank_energy(eos, den, pres, Gd);
+  double dedG[9], GdedG[9];
+  for (int i = 0; i < 9; ++i) dedG[i] = e.d[i];
+  matmul3(G, dedG, GdedG);
+  for (int i = 0; i < 9; ++i) sig[i] = (-2.0 * den) * GdedG[i];
+}
+
 // eigvals(ac) (HyperelasticityMPh.jl:263): cyclic Jacobi on (ac+ac')/2, ascending order
 // (Julia sorts eigvals of a general real matrix by (real, imag)).
 static void eigvals_sym3(const double* ac, double* ev) {
@@ -670,6 +715,13 @@ int hso_get_eigvals_n(const double* eos, const double* Q, const double* n, doubl
 double hso_energy(const double* eos, double S, const double* G) { return energy(*reinterpret_cast<const Eos*>(eos), S, G); }
 double hso_entropy(const double* eos, double e_int, const double* G) { return entropy(*reinterpret_cast<const Eos*>(eos), e_int, G); }
 void hso_finger(const double* F, double* G) { finger(F, G); }
+// Hank2016: per-item scalar calls; return 1 where Julia would throw DomainError
+int hso_hank_energy(const double* eos, double den, double pres, const double* G, double* e) {
+  g_domain_error = 0; *e = hank_energy(*reinterpret_cast<const Hank*>(eos), den, pres, G); return g_domain_error; }
+int hso_hank_pressure(const double* eos, double den, double e_int, const double* inv3, double* p) {
+  g_domain_error = 0; *p = hank_pressure(*reinterpret_cast<const Hank*>(eos), den, e_int, inv3); return g_domain_error; }
+int hso_hank_stress(const double* eos, double den, double pres, const double* A, double* sig) {
+  g_domain_error = 0; hank_stress(*reinterpret_cast<const Hank*>(eos), den, pres, A, sig); return g_domain_error; }
 void hso_invariants(const double* G, double* i3) { invariants(G, i3); }
 void hso_stress(const double* eos, double S, const double* F, double* sig) { stress(*reinterpret_cast<const Eos*>(eos), S, F, sig); }
 void hso_acoustic(const double* eos, double S, const double* F, const double* n, double* ac) {

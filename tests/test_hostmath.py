@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def hm():
     so = os.path.join(HERE, "hostmath", "libhostmath.so")
     src = os.path.join(HERE, "hostmath", "hostmath.cpp")
-    hdr = os.path.join(HERE, "..", "hyperelasticsolver_b200", "csrc", "hs_phase.cuh")
-    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+    hdrs = [os.path.join(HERE, "..", "hyperelasticsolver_b200", "csrc", h) for h in ("hs_phase.cuh", "hs_hank.cuh")]
+    if not os.path.exists(so) or max(os.path.getmtime(f) for f in [src] + hdrs) > os.path.getmtime(so):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
     lib = C.CDLL(so)
     dp = C.POINTER(C.c_double)
@@ -114,3 +114,38 @@ def test_acoustic_general_normal(hm, oracle):
             ref = 0.5 * (ac + ac.T)
             r6 = np.array([ref[0, 0], ref[0, 1], ref[0, 2], ref[1, 1], ref[1, 2], ref[2, 2]])
             assert np.abs(S6 - r6).max() < 1e-12 * np.abs(r6).max()
+
+
+def test_hank2016_closed_forms_vs_dual_oracle(hm, oracle):
+    """hs_hank.cuh (what k_hank runs) against the literal dual-number restatement of EquationsOfState.jl:301-356"""
+    dp = C.POINTER(C.c_double)
+    hm.hm_hank_energy.argtypes = [dp, C.c_double, C.c_double, dp, dp]
+    hm.hm_hank_pressure.argtypes = [dp, C.c_double, C.c_double, dp, dp]
+    hm.hm_hank_stress.argtypes = [dp, C.c_double, dp, dp]
+    rng = np.random.default_rng(7)
+    for eos in (oracle.hank2016(), oracle.hank2016(rho0=8.9, mu=48e9, gamma=4.2, pres_inf=34e9, a=-0.3), oracle.hank2016(a=1.0)):
+        for it in range(100):
+            A = np.eye(3) + 0.2 * rng.uniform(-1, 1, (3, 3))
+            a9 = np.ascontiguousarray(A.flatten(order="F"))
+            den = eos[0] * abs(np.linalg.det(A)) * rng.uniform(0.9, 1.1)
+            pres = rng.uniform(-1e9, 5e10)
+            G = A.T @ A
+            g9 = np.ascontiguousarray(G.flatten(order="F"))
+            inv3 = oracle.invariants(g9)
+            e_o, st = oracle.hank_energy(eos, den, pres, g9); assert st == 0
+            out = np.zeros(1)
+            assert hm.hm_hank_energy(_p(eos), den, pres, _p(g9), _p(out)) == 0
+            assert abs(out[0] - e_o) <= 1e-13 * abs(e_o)
+            p_o, st = oracle.hank_pressure(eos, den, e_o, inv3); assert st == 0
+            assert hm.hm_hank_pressure(_p(eos), den, e_o, _p(inv3), _p(out)) == 0
+            assert abs(out[0] - p_o) <= 1e-12 * max(abs(p_o), eos[2] * eos[3])
+            assert abs(p_o - pres) <= 1e-12 * eos[2] * eos[3]            # pressure inverts energy
+            s_o, st = oracle.hank_stress(eos, den, pres, a9); assert st == 0
+            sig = np.zeros(9)
+            assert hm.hm_hank_stress(_p(eos), den, _p(a9), _p(sig)) == 0
+            assert np.abs(sig - s_o).max() <= 1e-12 * max(np.abs(s_o).max(), 1e-3 * eos[1])
+    # domain: det G <= 0 is where Julia's fractional power throws
+    bad = np.diag([1.0, 1.0, -1.0]).flatten()
+    out = np.zeros(1)
+    assert hm.hm_hank_energy(_p(eos), 2.7, 1e9, _p(bad), _p(out)) == 1
+    assert oracle.hank_energy(eos, 2.7, 1e9, bad)[1] == 1

@@ -156,3 +156,38 @@ def test_sp_matches_mph_identical_phases(oracle):
     got = rm["Q"].copy(); want = sp_to_mph(rs["Q"])
     got[:, [1, 16]] = 0.0     # alpha*rho is passive and absent from the 13-variable model
     assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+
+
+def test_hank2016_oracle_anchors(oracle):
+    """Hank2016 (EquationsOfState.jl:301-356) is dead code without tests in the reference: the restatement is
+    anchored on what the formulas imply -- zero elastic energy and stress in the undeformed state, a trace-free
+    stress, the small-strain shear response sigma = -2 (den/rho0) mu eps for distortion 1 + eps, pressure as the
+    inverse of energy, and the dual-number gradient against central differences."""
+    eos = oracle.hank2016()
+    rho0, mu, gamma, pinf, a = eos
+    I9 = np.eye(3).flatten()
+    e, st = oracle.hank_energy(eos, rho0, 1e9, I9)
+    assert st == 0 and abs(e - (1e9 + gamma * pinf) / (rho0 * (gamma - 1))) < 1e-6
+    s, _ = oracle.hank_stress(eos, rho0, 1e9, I9)
+    assert np.abs(s).max() < 1e-14 * mu                                    # roundoff of mu
+    rng = np.random.default_rng(11)
+    for it in range(20):
+        A = np.eye(3) + 0.15 * rng.uniform(-1, 1, (3, 3)); a9 = A.flatten(order="F")
+        den = rho0 * np.linalg.det(A)
+        s, st = oracle.hank_stress(eos, den, 3e9, a9); S = s.reshape(3, 3, order="F")
+        assert st == 0 and abs(np.trace(S)) < 1e-12 * np.abs(S).max()
+        assert np.abs(S - S.T).max() < 1e-12 * np.abs(S).max()
+        # central differences of energy over the 9 entries of G, then -2 den G de/dG
+        G = (A.T @ A)
+        g9 = G.flatten(order="F"); h = 1e-6; d = np.zeros(9)
+        for k in range(9):
+            gp = g9.copy(); gm = g9.copy(); gp[k] += h; gm[k] -= h
+            d[k] = (oracle.hank_energy(eos, den, 3e9, gp)[0] - oracle.hank_energy(eos, den, 3e9, gm)[0]) / (2 * h)
+        fd = -2 * den * G @ d.reshape(3, 3, order="F")
+        assert np.abs(fd - S).max() < 2e-5 * np.abs(S).max()
+        g_inv = oracle.invariants(g9)
+        e, _ = oracle.hank_energy(eos, den, 3e9, g9)
+        assert abs(oracle.hank_pressure(eos, den, e, g_inv)[0] - 3e9) < 1e-12 * gamma * pinf
+    eps = 1e-7 * np.array([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
+    s, _ = oracle.hank_stress(eos, rho0, 0.0, (np.eye(3) + eps).flatten(order="F"))
+    assert abs(s.reshape(3, 3)[0, 1] - (-2 * mu * 1e-7)) < 1e-6 * 2 * mu * 1e-7
