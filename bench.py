@@ -303,7 +303,7 @@ def run_ours(args):
                            else "k_step (fused path-conservative flux + update + next-step wave bounds)"), "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_cell_update": 2 * nvar * 8, "cell_updates_per_launch": updated_local, "peak_source": peak_src,
                 "fp64_pipe_pct_ncu": fp64_pct, "fp64_issue_peak_dfma_per_s": 1.708e13,
-                "note": ("single-phase: DRAM traffic (algorithmic 208 B + 96 B of cached per-cell rows per cell update) and FP64 issue are both near their limits (DESIGN.md)"
+                "note": ("single-phase: DRAM traffic (algorithmic 208 B + 80 B of cached per-cell rows per cell update) and instruction issue are both near their limits (DESIGN.md)"
                          if model == "sp13" else "two-phase: FP64-pipe bound, not HBM bound (DESIGN.md): see profiles/ for the measured DFMA peak and pipe utilisation")}
 
     # ---- end to end through the host-buffer API ------------------------------------------------

@@ -18,7 +18,7 @@ SP13, MPH30 = 0, 1
 LXF, HLL = 0, 1
 NVAR = {SP13: 13, MPH30: 30}
 NPHASE = {SP13: 1, MPH30: 2}
-NAUX = {SP13: 6, MPH30: 2}   # HS_NAUX(model): cached per-cell rows (wave bounds; SP also 1/rho and stress row 1)
+NAUX = {SP13: 5, MPH30: 2}   # HS_NAUX(model): cached per-cell rows (SP: c_max, 1/rho, stress row 1; MPh: wave bounds); re-read from the library in lib()
 HS_SCAL_SLOTS = 8
 
 
@@ -99,6 +99,7 @@ SIGNATURES = {
                            _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
     "hsd_halo": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "hsd_mailbox_doubles": (C.c_int, []),
+    "hsd_naux": (C.c_int, [C.c_int]),
     "hsd_exchange_p2p": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_uint64, _vp, _vp]),
     "hsd_scal_lambda_next": (_vp, [_vp, _i64, _i64]),
     "hsd_scal_lambda_cur": (_vp, [_vp, _i64, _i64]),
@@ -132,6 +133,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
+        NAUX[SP13], NAUX[MPH30] = L.hsd_naux(SP13), L.hsd_naux(MPH30)   # the layout the library was built with
         _lib = L
     return _lib
 

@@ -120,8 +120,15 @@ bool make_tile_map(CUtensorMap* m, const double* base, long long stride, int row
   const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(double)};
   const cuuint32_t box[2] = {128u, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1u, 1u};
+  // L2 promotion of the tile reads: 128 B by default; HS_SP_L2PROMO=0 / 64 / 256 for tuning runs
+  static const CUtensorMapL2promotion promo = [] {
+    const char* e = std::getenv("HS_SP_L2PROMO");
+    const int v = e ? std::atoi(e) : 128;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  }();
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Single-phase TMA tile pipeline (k_step_sp): every block walks over `kper` tiles.
@@ -152,7 +159,7 @@ int launch_step_sp(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st)
   CUtensorMap mq, ma;
   std::memset(&mq, 0, sizeof mq); std::memset(&ma, 0, sizeof ma);
   const bool tm2d = !(e2 && e2[0] == '0') && (a.stride % 2 == 0) && a.stride < 0x7fffffffLL &&
-                    make_tile_map(&mq, a.Qin, a.stride, 13) && make_tile_map(&ma, a.aux_in, a.stride, 6);
+                    make_tile_map(&mq, a.Qin, a.stride, 13) && make_tile_map(&ma, a.aux_in, a.stride, SP_NAX);
   if (tm2d) {
     if (single) return launch_step_sp_s<FLUX, GEN, T, true, true>(a, ntiles, kper, mq, ma, st);
     return launch_step_sp_s<FLUX, GEN, T, false, true>(a, ntiles, kper, mq, ma, st);
@@ -314,6 +321,8 @@ int hsd_halo(const hsd_problem_t* p, double* Q, double* aux, double* left, doubl
   return HS_OK;
 }
 
+static_assert(HS_NAUX(HS_MODEL_SP13) == SP_NAX && HS_NAUX(HS_MODEL_MPH30) == ModelTraits<MODEL_MPH30>::NAUX, "header and kernels disagree on the cache rows");
+int hsd_naux(int model) { return HS_NAUX(model); }
 int hsd_mailbox_doubles(void) { return 2 * MBOX_STRIDE; }
 
 int hsd_exchange_p2p(const hsd_problem_t* p, double* Q, double* aux, double* lam_slot, void* const* mailboxes, int rank, int world,

@@ -76,7 +76,17 @@ template <int MODEL> struct ModelTraits;
 // get_eigvals keeps).  The single-phase model also caches 1/rho and row 1 of the stress (rows 2..5):
 // the CFL sweep at the end of a step computes them anyway, and with them the next step's physical
 // flux needs no state recovery (saves ~20 % of the FP64 work for 32 B/cell more traffic each way).
-template <> struct ModelTraits<MODEL_SP13> { static constexpr int NPH = 1, NVAR = 13, J0 = 2, NAUX = 6; };
+// HS_SP_CROW = 1: the single-phase model caches ONE wave-speed row, c_max, instead of the two bounds lo / hi = u1 -+ c_max
+// (rows: 0 c_max, 1 1/rho, 2..4 stress row 1).  u1 = m1 * (1/rho) is the very product the flux forms anyway and 1/rho is cached, so
+// the bounds come back bit-identical (the product is rounded on its own, __dmul_rn, exactly as phase_state rounds u1 before it
+// subtracts) for 16 B less DRAM traffic per cell-update and no extra instruction.
+#ifndef HS_SP_CROW
+#define HS_SP_CROW 1   // (include/hyperelastic_b200.h sets the same default; hs_api.cu asserts that the two agree)
+#endif
+constexpr bool SP_CROW = HS_SP_CROW != 0;
+constexpr int SP_R_ID = SP_CROW ? 1 : 2;   // cache row of 1/rho
+constexpr int SP_R_SG = SP_CROW ? 2 : 3;   // first cache row of the stress row
+template <> struct ModelTraits<MODEL_SP13> { static constexpr int NPH = 1, NVAR = 13, J0 = 2, NAUX = SP_CROW ? 5 : 6; };
 template <> struct ModelTraits<MODEL_MPH30> { static constexpr int NPH = 2, NVAR = 30, J0 = 0, NAUX = 2; };
 
 // physical flux of the single-phase record from the cached 1/rho and stress row (same expressions as
@@ -346,10 +356,18 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 #pragma unroll
     for (int v = 0; v < 13; ++v) rin[sp_slot(v)] = __ldg(g.Qin + (size_t)v * g.stride + gi);
   }
-  if (ph == 0) { lo_in_r = __ldg(g.aux_in + gi); hi_in_r = __ldg(g.aux_in + g.stride + gi); }
+  constexpr bool CROW = SP_CROW && MODEL == MODEL_SP13;
+  static_assert(!CROW || SPC, "the c_max row needs the cached 1/rho");
+  double c_in_r = 0.0;
+  if (CROW) c_in_r = __ldg(g.aux_in + gi);
+  else if (ph == 0) { lo_in_r = __ldg(g.aux_in + gi); hi_in_r = __ldg(g.aux_in + g.stride + gi); }
   if (SPC) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) ax[r] = __ldg(g.aux_in + (size_t)(2 + r) * g.stride + gi);
+    for (int r = 0; r < 4; ++r) ax[r] = __ldg(g.aux_in + (size_t)(SP_R_ID + r) * g.stride + gi);
+  }
+  if (CROW) {
+    const double u1 = __dmul_rn(rin[2], ax[0]);   // u1 as phase_state rounds it (no contraction into the add)
+    lo_in_r = u1 - c_in_r; hi_in_r = u1 + c_in_r;
   }
 
   const bool own_interior = valid && l >= 1 && l <= CPB - 2 && c <= g.ncells - 2;
@@ -384,10 +402,11 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 #pragma unroll
         for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = Rs[sp_slot(v) * T + tid];
       }
-      if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
+      if (CROW) g.aux_out[gi] = c_in_r;
+      else if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
       if (SPC) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) g.aux_out[(size_t)(2 + r) * g.stride + gi] = ax[r];
+        for (int r = 0; r < 4; ++r) g.aux_out[(size_t)(SP_R_ID + r) * g.stride + gi] = ax[r];
       }
     }
     if (tile == 0 && tid == 0) {
@@ -479,18 +498,20 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     }
     if (own_interior) {
       bad |= sn.bad;
-      if (ph == 0) { g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n; }
+      if (CROW) g.aux_out[gi] = cn;
+      else if (ph == 0) { g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n; }
       if (SPC) {
-        g.aux_out[(size_t)2 * g.stride + gi] = sn.inv_den;
+        g.aux_out[(size_t)SP_R_ID * g.stride + gi] = sn.inv_den;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) g.aux_out[(size_t)(3 + r) * g.stride + gi] = sn.sig1[r];
+        for (int r = 0; r < 3; ++r) g.aux_out[(size_t)(SP_R_SG + r) * g.stride + gi] = sn.sig1[r];
       }
       lamv = fmax(fabs(lo_n), fabs(hi_n));
     } else if (own_frozen) {
-      if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
+      if (CROW) g.aux_out[gi] = c_in_r;
+      else if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
       if (SPC) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) g.aux_out[(size_t)(2 + r) * g.stride + gi] = ax[r];
+        for (int r = 0; r < 4; ++r) g.aux_out[(size_t)(SP_R_ID + r) * g.stride + gi] = ax[r];
       }
       lamv = fmax(fabs(lo_s[l]), fabs(hi_s[l]));
     }
@@ -579,7 +600,8 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v) { asm volatile(
 }  // namespace tma
 
 constexpr int SP_TS = 130;                       // doubles per stage row: 128 cells + alignment slack
-constexpr int SP_NST = 19;                       // rows per stage: 13 state rows (slots 2..14) + 6 cache rows
+constexpr int SP_NAX = ModelTraits<MODEL_SP13>::NAUX;   // cache rows per cell (6, or 5 with HS_SP_CROW)
+constexpr int SP_NST = 13 + SP_NAX;              // rows per stage: 13 state rows (slots 2..14) + the cache rows
 constexpr unsigned SP_ROW_BYTES = SP_TS * 8, SP_STAGE_BYTES = SP_NST * SP_ROW_BYTES;
 // SP13 variable stored in record slot j (inverse of sp_slot)
 __host__ __device__ constexpr int sp_var(int j) { return j < 5 ? j - 2 : (j == 5 ? 12 : 3 + 3 * ((j - 6) % 3) + (j - 6) / 3); }
@@ -719,7 +741,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 #pragma unroll
       for (int v = 0; v < 13; ++v) SQ(sp_slot(v), tid) = __ldg(g.Qin + (size_t)v * g.stride + gi);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) SA(r, tid) = __ldg(g.aux_in + (size_t)r * g.stride + gi);
+      for (int r = 0; r < SP_NAX; ++r) SA(r, tid) = __ldg(g.aux_in + (size_t)r * g.stride + gi);
       __syncthreads();
     }
 
@@ -748,8 +770,11 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
         fbad = sm.bad;
         const double cm = phase_cmax<true>(eos, sm);
         const double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
-        s_l = fmin(0.0, fmin(lo_m, SA(0, L)));
-        s_r = fmax(0.0, fmax(hi_m, SA(1, tid)));
+        // cached bounds of the two cells (the `eigvals` argument, NumFluxes.jl:90-91); with the c_max row: u1 -+ c_max
+        const double lo_l = SP_CROW ? __dmul_rn(SQ(2, L), SA(SP_R_ID, L)) - SA(0, L) : SA(0, L);
+        const double hi_r = SP_CROW ? __dmul_rn(SQ(2, tid), SA(SP_R_ID, tid)) + SA(0, tid) : SA(1, tid);
+        s_l = fmin(0.0, fmin(lo_m, lo_l));
+        s_r = fmax(0.0, fmax(hi_m, hi_r));
         inv_ds = hs_rcp(s_r - s_l);
         k_q = s_l * s_r * inv_ds;
         s_l *= inv_ds; s_r *= inv_ds;                     // weights of F_l and F_r in the HLL flux
@@ -759,9 +784,10 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 #pragma unroll
       for (int j = 2; j < 15; ++j) { ra[j] = SQ(j, L); q[j] = SQ(j, tid); }
       {
-        const double sl[3] = {SA(3, L), SA(4, L), SA(5, L)}, sr[3] = {SA(3, tid), SA(4, tid), SA(5, tid)};
-        sp_flux_cached(ra, SA(2, L), sl, fa);
-        sp_flux_cached(q, SA(2, tid), sr, fb);
+        const double sl[3] = {SA(SP_R_SG, L), SA(SP_R_SG + 1, L), SA(SP_R_SG + 2, L)};
+        const double sr[3] = {SA(SP_R_SG, tid), SA(SP_R_SG + 1, tid), SA(SP_R_SG + 2, tid)};
+        sp_flux_cached(ra, SA(SP_R_ID, L), sl, fa);
+        sp_flux_cached(q, SA(SP_R_ID, tid), sr, fb);
       }
 #pragma unroll
       for (int j = 2; j < 15; ++j) {
@@ -779,14 +805,19 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 #pragma unroll
         for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = q[sp_slot(v)];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) g.aux_out[(size_t)r * g.stride + gi] = SA(r, tid);
-        lamv = fmax(fabs(SA(0, tid)), fabs(SA(1, tid)));
+        for (int r = 0; r < SP_NAX; ++r) g.aux_out[(size_t)r * g.stride + gi] = SA(r, tid);
+        if (SP_CROW) {
+          const double u1 = __dmul_rn(q[2], SA(SP_R_ID, tid));
+          lamv = fmax(fabs(u1 - SA(0, tid)), fabs(u1 + SA(0, tid)));
+        } else {
+          lamv = fmax(fabs(SA(0, tid)), fabs(SA(1, tid)));
+        }
       }
     } else if (own_interior || own_frozen) {   // this problem already reached t_end: carry it through unchanged
 #pragma unroll
       for (int v = 0; v < 13; ++v) g.Qout[(size_t)v * g.stride + gi] = SQ(sp_slot(v), tid);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) g.aux_out[(size_t)r * g.stride + gi] = SA(r, tid);
+      for (int r = 0; r < SP_NAX; ++r) g.aux_out[(size_t)r * g.stride + gi] = SA(r, tid);
     }
     if (tid == 32 && new_prob) write_scalars(sc + ((sci + 1) % 3) * 8, lam_n, t_n);
     if (tid == 0) {
@@ -823,10 +854,11 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       const double lo_n = sn.u[0] - cn, hi_n = sn.u[0] + cn;
       if (own_interior) {
         bad |= sn.bad;
-        g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n;
-        g.aux_out[(size_t)2 * g.stride + gi] = sn.inv_den;
+        if (SP_CROW) g.aux_out[gi] = cn;
+        else { g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n; }
+        g.aux_out[(size_t)SP_R_ID * g.stride + gi] = sn.inv_den;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) g.aux_out[(size_t)(3 + r) * g.stride + gi] = sn.sig1[r];
+        for (int r = 0; r < 3; ++r) g.aux_out[(size_t)(SP_R_SG + r) * g.stride + gi] = sn.sig1[r];
         lamv = fabs(sn.u[0]) + cn;                        // = max(|lo_n|, |hi_n|), bit for bit (rounding is monotone and odd)
       }
       lam_run = fmax(lam_run, lamv);
@@ -902,11 +934,12 @@ __global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, doub
   int bad = 0;
   if (valid) {
     bad = st.bad;
-    if (ph == 0) { aux[gi] = lo_c; aux[stride + gi] = hi_c; }
+    if (SP_CROW && MODEL == MODEL_SP13) aux[gi] = cm;
+    else if (ph == 0) { aux[gi] = lo_c; aux[stride + gi] = hi_c; }
     if (MODEL == MODEL_SP13) {
-      aux[(size_t)2 * stride + gi] = st.inv_den;
+      aux[(size_t)SP_R_ID * stride + gi] = st.inv_den;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) aux[(size_t)(3 + r) * stride + gi] = st.sig1[r];
+      for (int r = 0; r < 3; ++r) aux[(size_t)(SP_R_SG + r) * stride + gi] = st.sig1[r];
     }
     lamv = fmax(fabs(lo_c), fabs(hi_c));
     if (eig_full) {  // [u1 + c_k (ascending), u1 - c_k], HyperelasticityMPh.jl:263-265

@@ -42,12 +42,12 @@ class CudaKernels:
     """The product kernels behind the device-pointer ABI (hsd_*), on torch's current stream."""
 
     def __init__(self, eos, model, device):
+        self._lib = L.lib()             # (also fills L.NAUX with the layout the library was built with)
         self.model = model
         self.nvar = L.NVAR[model]
         self.naux = L.NAUX[model]
         self.device = torch.device(device)
         self._eos = L.eos_array(eos, model)
-        self._lib = L.lib()
         if self._lib.hs_device_count() <= 0:
             raise L.HyperelasticError(L.HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback")
 

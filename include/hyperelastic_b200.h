@@ -157,13 +157,20 @@ int hs_selftest_eig(const double* s6, double* lam_max_abs, int64_t n, int device
  * one-process-per-GPU driver uses so that halo exchange / allreduce (NCCL through
  * torch.distributed) can be enqueued on the same stream between steps.
  *   Q      : [nvar][stride] doubles, stride = ncells*nprob (cell index = prob*ncells + i)
- *   aux    : [HS_NAUX(model)][stride] cached per-cell rows: 0/1 = wave bounds min/max over phases of
- *            u1 -+ c_max; single-phase rows 2..5 = 1/rho and row 1 of the stress (what the next
- *            step's physical flux needs, so it can skip the state recovery)
+ *   aux    : [HS_NAUX(model)][stride] cached per-cell rows.  Two-phase: 0/1 = wave bounds min/max over phases of
+ *            u1 -+ c_max.  Single-phase: row 0 = c_max (the bounds are u1 -+ c_max with u1 = m1 * (1/rho), bit-identical
+ *            to caching them), rows 1..4 = 1/rho and row 1 of the stress (what the next step's physical flux
+ *            needs, so it can skip the state recovery)
  *   scal   : HS_SCAL_DOUBLES(nprob) doubles of per-problem scalars (lambda_max x3 slots, t x3
  *            slots, step count, status); opaque, zero-initialise, see hsd_scal_* helpers
  * ------------------------------------------------------------------------------------------ */
-#define HS_NAUX(model) ((model) == HS_MODEL_SP13 ? 6 : 2)
+/* HS_SP_CROW (build option, default 1): the single-phase model caches ONE wave-speed row, c_max, instead of the two bounds
+ * lo / hi = u1 -+ c_max -- rows [c_max, 1/rho, stress row 1(3)]; 0 restores [lo, hi, 1/rho, stress row 1(3)]. */
+#ifndef HS_SP_CROW
+#define HS_SP_CROW 1
+#endif
+#define HS_NAUX_SP (HS_SP_CROW ? 5 : 6)
+#define HS_NAUX(model) ((model) == HS_MODEL_SP13 ? HS_NAUX_SP : 2)
 #define HS_SCAL_SLOTS 8
 #define HS_SCAL_DOUBLES(nprob) (HS_SCAL_SLOTS * (nprob) + 8)
 
@@ -202,6 +209,8 @@ int hsd_halo(const hsd_problem_t* p, double* Q, double* aux, double* left, doubl
  * hang the GPU: after HS_EXCHANGE_TIMEOUT_S seconds (default 20) the kernel gives up and sets bit 1 of the
  * status word of `scal`. */
 int hsd_mailbox_doubles(void);
+/* HS_NAUX(model) of the library as built (a host binding sizes its aux arrays with this) */
+int hsd_naux(int model);
 int hsd_exchange_p2p(const hsd_problem_t* p, double* Q, double* aux, double* lam_slot, void* const* mailboxes, int rank, int world,
                      uint64_t seq, double* scal, void* stream);
 /* address (device pointer) of the lambda_max slot that step n WRITES, as doubles [nprob]:

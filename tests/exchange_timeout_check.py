@@ -16,7 +16,7 @@ eos = hs.Barton2009()
 k = CudaKernels(eos, hs.SP13, "cuda:0")
 n = 64
 prob = k.problem(n, 1)
-Q = k.zeros(13, n); aux = k.zeros(6, n); scal = k.zeros(scal_size(1))
+Q = k.zeros(13, n); aux = k.zeros(k.naux, n); scal = k.zeros(scal_size(1))
 mine = k.zeros(k.mailbox_doubles()); dead = k.zeros(k.mailbox_doubles())     # the "peer" never posts
 t0 = time.perf_counter()
 k.exchange_p2p(prob, Q, aux, scal[1:2], [mine.data_ptr(), dead.data_ptr()], 0, 2, 1, scal)
