@@ -35,6 +35,21 @@ def test_struct_layouts(hs):
     assert C.sizeof(L.HsdProblem) == 4 * 4 + 3 * 8 + 2 * 20 * 8
 
 
+def test_cache_row_count_matches_header(hs):
+    """hsd_naux() (the layout the library was built with) == HS_NAUX of the header at its default build option;
+    the Hank2016 block is 5 doubles in the reference's field order."""
+    from hyperelasticsolver_b200 import _lib as L
+    txt = open(os.path.join(ROOT, "include", "hyperelastic_b200.h")).read()
+    crow = int(re.search(r"#ifndef HS_SP_CROW\s*\n#define HS_SP_CROW (\d)", txt).group(1))
+    assert "#define HS_NAUX_SP (HS_SP_CROW ? 5 : 6)" in txt
+    lib = L.lib()
+    assert lib.hsd_naux(L.SP13) == (5 if crow else 6) == L.NAUX[L.SP13]
+    assert lib.hsd_naux(L.MPH30) == 2 == L.NAUX[L.MPH30]
+    assert C.sizeof(L.Hank2016) == 40
+    h = L.Hank2016()
+    assert (h.rho0, h.mu, h.gamma, h.pres_inf, h.a) == (2.7, 26e9, 3.4, 21.5e9, 0.5)   # EquationsOfState.jl:312-318
+
+
 def test_problem_init_and_arg_errors(hs):
     from hyperelasticsolver_b200 import _lib as L
     lib = L.lib()
