@@ -9,7 +9,7 @@ routine Julia's `eigvals` dispatches to for a general real matrix).
 Each function cites the reference file:line it follows.  PARITY UNPINNED against the real
 Julia reference (no Julia here, no golden vectors shipped) -- see oracle/README.md.
 
-Run `python oracle/pyoracle.py` to (re)generate tests/golden/pyoracle_vectors.json.
+Run `python oracle/pyoracle.py` to (re)generate tests/golden/pyoracle_vectors.json and pyoracle_hank_vectors.json.
 """
 from __future__ import annotations
 
@@ -184,6 +184,58 @@ def noncons_cols(eoss, Q):  # HyperelasticityMPh.jl:178-250 (column 1 of each bl
 
 
 # ---------------------------------------------------------------------------------------------
+# Hank2016, EquationsOfState.jl:301-356 (dead code in the reference; a 3x3 tensor is read as its 9 column-major
+# entries, see oracle.cpp).  Gradient by reverse-mode autograd.
+class Hank2016:
+    def __init__(self, rho0=2.7, mu=26e9, gamma=3.4, pres_inf=21.5e9, a=0.5):
+        self.rho0, self.mu, self.gamma, self.pres_inf, self.a = rho0, mu, gamma, pres_inf, a
+
+    def block(self):
+        return [float(v) for v in (self.rho0, self.mu, self.gamma, self.pres_inf, self.a)]
+
+
+def hank_e_el(eos, i1, i2, i3):  # EquationsOfState.jl:326-328
+    j1 = i1 / i3 ** (1 / 3)
+    j2 = (i1 ** 2 - 2 * i2) / i3 ** (2 / 3)
+    return eos.mu / (4 * eos.rho0) * ((1 - 2 * eos.a) / 3 * j1 ** 2 + eos.a * j2 + 3 * (eos.a - 1))
+
+
+def hank_energy(eos, den, pres, G):  # EquationsOfState.jl:317-331
+    return hank_e_el(eos, *invariants(G)) + (pres + eos.gamma * eos.pres_inf) / (den * (eos.gamma - 1))
+
+
+def hank_pressure(eos, den, e_int, inv3):  # EquationsOfState.jl:333-346
+    return (e_int - hank_e_el(eos, *inv3)) * (eos.gamma - 1) * den - eos.gamma * eos.pres_inf
+
+
+def hank_stress(eos, den, pres, distortion):  # EquationsOfState.jl:348-356
+    G = finger(vec(torch.linalg.inv(mat(distortion)))).detach().requires_grad_(True)
+    e = hank_energy(eos, den, pres, G)
+    (dedG,) = torch.autograd.grad(e, G)
+    return vec(-2.0 * den * mat(G.detach()) @ mat(dedG))
+
+
+def generate_hank(path):
+    rng = np.random.default_rng(20261018)
+    doc = {"generator": "oracle/pyoracle.py::generate_hank (torch reverse-mode autograd)", "cases": []}
+    for eos in (Hank2016(), Hank2016(rho0=8.9, mu=48e9, gamma=4.2, pres_inf=34e9, a=-0.3)):
+        for k in range(6):
+            A = np.eye(3) + 0.2 * rng.uniform(-1, 1, (3, 3))
+            a9 = torch.tensor(A.flatten(order="F"))
+            den = float(eos.rho0 * abs(np.linalg.det(A)) * rng.uniform(0.9, 1.1)); pres = float(rng.uniform(-1e9, 5e10))
+            g9 = vec(mat(a9).T @ mat(a9))
+            i1, i2, i3 = invariants(g9)
+            e = hank_energy(eos, den, pres, g9)
+            doc["cases"].append({"eos_block": eos.block(), "distortion": a9.tolist(), "den": den, "pres": pres, "G": g9.tolist(),
+                                 "invariants": [float(i1), float(i2), float(i3)], "energy": float(e),
+                                 "pressure": float(hank_pressure(eos, den, e, (i1, i2, i3))),
+                                 "stress": hank_stress(eos, den, pres, a9).tolist()})
+    with open(path, "w") as f:
+        json.dump(doc, f, indent=0)
+    return doc
+
+
+# ---------------------------------------------------------------------------------------------
 def _states():
     rng = np.random.default_rng(20261017)
     out = []
@@ -229,4 +281,7 @@ if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
     p = os.path.join(os.path.dirname(here), "tests", "golden", "pyoracle_vectors.json")
     d = generate(p)
+    print("wrote", p, len(d["cases"]), "cases")
+    p = os.path.join(os.path.dirname(here), "tests", "golden", "pyoracle_hank_vectors.json")
+    d = generate_hank(p)
     print("wrote", p, len(d["cases"]), "cases")

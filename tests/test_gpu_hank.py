@@ -61,3 +61,16 @@ def test_hank2016_edge_cases(gpu, oracle):
         E.energy(gpu.Barton2009(), 1.0, 1.0, np.eye(3))
     rc = gpu.lib().hs_hank2016_energy(None, None, None, None, None, 1, 0)
     assert rc == 1                                                             # HS_ERR_ARG
+
+
+def test_hank2016_golden_vectors(gpu):
+    """the committed torch-autograd vectors (oracle/pyoracle.py::generate_hank) through the C ABI"""
+    import json, os
+    E = gpu.equations_of_state
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyoracle_hank_vectors.json")))
+    for c in d["cases"]:
+        eos = gpu.Hank2016(*c["eos_block"])
+        assert abs(E.energy(eos, c["den"], c["pres"], np.array(c["G"])) - c["energy"]) <= 1e-13 * abs(c["energy"])
+        assert abs(E.pressure(eos, c["den"], c["energy"], np.array(c["invariants"])) - c["pressure"]) <= 1e-12 * eos.gamma * eos.pres_inf
+        s = E.stress(eos, c["den"], c["pres"], np.array(c["distortion"]))
+        assert np.abs(s - np.array(c["stress"])).max() <= 1e-12 * np.abs(c["stress"]).max()

@@ -191,3 +191,18 @@ def test_hank2016_oracle_anchors(oracle):
     eps = 1e-7 * np.array([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 0.0]])
     s, _ = oracle.hank_stress(eos, rho0, 0.0, (np.eye(3) + eps).flatten(order="F"))
     assert abs(s.reshape(3, 3)[0, 1] - (-2 * mu * 1e-7)) < 1e-6 * 2 * mu * 1e-7
+
+
+def test_hank2016_against_pyoracle_vectors(oracle):
+    """C++ dual-number Hank2016 vs the torch reverse-mode restatement (tests/golden/pyoracle_hank_vectors.json)"""
+    d = json.load(open(os.path.join(G, "pyoracle_hank_vectors.json")))
+    assert len(d["cases"]) >= 12
+    for c in d["cases"]:
+        eos = np.array(c["eos_block"])
+        e, st = oracle.hank_energy(eos, c["den"], c["pres"], np.array(c["G"]))
+        assert st == 0 and abs(e - c["energy"]) <= 1e-13 * abs(c["energy"])
+        assert np.abs(oracle.invariants(np.array(c["G"])) - np.array(c["invariants"])).max() <= 1e-13 * max(np.abs(c["invariants"]))
+        p, st = oracle.hank_pressure(eos, c["den"], c["energy"], np.array(c["invariants"]))
+        assert st == 0 and abs(p - c["pressure"]) <= 1e-12 * eos[2] * eos[3]
+        s_, st = oracle.hank_stress(eos, c["den"], c["pres"], np.array(c["distortion"]))
+        assert st == 0 and np.abs(s_ - np.array(c["stress"])).max() <= 1e-12 * np.abs(c["stress"]).max()
