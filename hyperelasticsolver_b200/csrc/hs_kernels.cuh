@@ -178,6 +178,11 @@ __device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const d
 //   FROM_END = false: psi(s) = base + s d          (base = start of the segment)
 //   FROM_END = true : psi(s) = base - (1 - s) d    (base = end of the segment)
 // i.e. one fused multiply-add per component instead of the two of Q_l (1-s) + Q_r s.  MPh only.
+// HS_PHASE_CH = 1 (tuning build, not yet measured on a GPU): quadrature states through phase_state_row1
+// (B = A A^T + Cayley-Hamilton, hs_phase.cuh) -- ~10 FP64 instructions fewer per state, results differ by a few ulp.
+#ifndef HS_PHASE_CH
+#define HS_PHASE_CH 0
+#endif
 template <bool GEN, int T, bool FROM_END>
 __device__ __forceinline__ void path_integral(const EosDev& eos, const double* base, const double* d, const double* xs,
                                               const double* ws, double* acc, int& bad) {
@@ -194,7 +199,11 @@ __device__ __forceinline__ void path_integral(const EosDev& eos, const double* b
 #pragma unroll
     for (int k = 0; k < 9; ++k) A[k] = fma(s, d[(6 + k) * T], base[(6 + k) * T]);
     PhaseState st;
+#if HS_PHASE_CH
+    phase_state_row1<GEN>(eos, alpha, m, E, A, st);
+#else
     phase_state<GEN>(eos, alpha, m, E, A, st);
+#endif
     bad |= st.bad;
     noncons_accumulate(st, A, w, acc);
   }

@@ -235,6 +235,72 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   s.sig1[2] = fma(am, G[2], -em * s.G2r1[2]);
 }
 
+// Row-1 flavour of phase_state for the quadrature states of the path integrals (tuning build HS_PHASE_CH, not yet measured on a
+// GPU; the default build does not use it).  The non-conservative column only needs u, T and row 1 of sigma, i.e. row 1 of G and
+// of G^2, tr G and J.  They come from B = A A^T without forming G:  G = kappa^2 cof(B) (row 1 and the diagonal of the cofactor
+// matrix only), G^-1 = B / den^2, I2 = I3 tr(G^-1) with I3 / den^2 = 1/(alpha rho0)^2, and by Cayley-Hamilton
+// G^2 = I1 G - I2 1 + I3 G^-1: about 10 FP64 instructions fewer per state for a few ulp of cancellation in G^2
+// (I1 G - I2 + I3 G^-1 ~ 3 - 3 + 1).  Sets everything noncons_accumulate reads; G[3..5], h22, h33, uc2, Sp are NOT set.
+template <bool GEN>
+HS_HD void phase_state_row1(const EosDev& eos, double alpha, const double* m, double E, const double* A, PhaseState& s) {
+  const double C11 = A[4] * A[8] - A[7] * A[5], C12 = A[7] * A[2] - A[1] * A[8], C13 = A[1] * A[5] - A[4] * A[2];
+  const double detA = A[0] * C11 + A[3] * C12 + A[6] * C13;
+  const double ia = hs_rcp(alpha);
+  const double ia2r = ia * ia * eos.inv_rho0;                 // 1/(alpha^2 rho0)
+  const double x = detA * (ia * ia2r);                        // det(A/alpha)/rho0 = rho^2
+  s.bad = !(x > 0.0);
+  const double rs = hs_rsqrt(x);                              // 1/rho
+  const double rho = x * rs;
+  s.alpha = alpha; s.inv_alpha = ia; s.rho = rho; s.den = alpha * rho; s.inv_den = ia * rs;
+  s.u[0] = m[0] * s.inv_den; s.u[1] = m[1] * s.inv_den; s.u[2] = m[2] * s.inv_den;
+  s.Etot = E * s.inv_den;
+  const double e_int = s.Etot - 0.5 * (s.u[0] * s.u[0] + s.u[1] * s.u[1] + s.u[2] * s.u[2]);
+  const double kap = rs * ia2r, k2 = kap * kap;
+  // B = A A^T (B_ij = sum_k A_ik A_jk), symmetric; K = the cofactors of B that are needed
+  const double B11 = A[0] * A[0] + A[3] * A[3] + A[6] * A[6], B12 = A[0] * A[1] + A[3] * A[4] + A[6] * A[7];
+  const double B13 = A[0] * A[2] + A[3] * A[5] + A[6] * A[8], B22 = A[1] * A[1] + A[4] * A[4] + A[7] * A[7];
+  const double B23 = A[1] * A[2] + A[4] * A[5] + A[7] * A[8], B33 = A[2] * A[2] + A[5] * A[5] + A[8] * A[8];
+  const double K11 = B22 * B33 - B23 * B23, K22 = B11 * B33 - B13 * B13, K33 = B11 * B22 - B12 * B12;
+  const double K12 = B13 * B23 - B12 * B33, K13 = B12 * B23 - B13 * B22;
+  s.G[0] = k2 * K11; s.G[1] = k2 * K12; s.G[2] = k2 * K13;
+  s.G[3] = s.G[4] = s.G[5] = 0.0;
+  s.h22 = s.h33 = 0.0;
+  s.I1 = k2 * (K11 + K22 + K33);
+  const double gI = ia2r * eos.inv_rho0;                      // I3 / den^2:  I3 G^-1 = gI B
+  const double I2 = gI * (B11 + B22 + B33);
+  s.G2r1[0] = fma(s.I1, s.G[0], fma(gI, B11, -I2));
+  s.G2r1[1] = fma(s.I1, s.G[1], gI * B12);
+  s.G2r1[2] = fma(s.I1, s.G[2], gI * B13);
+  s.J = fma(s.I1 * s.I1, HS_LIT(third, 1.0 / 3.0), -I2);      // I1^2/3 - I2, EquationsOfState.jl:134 as written
+  const double r = rho * eos.inv_rho0;
+  double rA, rB, rC;
+  if (GEN) {
+    const double L = log(r);
+    rA = (eos.ea == 1.0) ? r : ((eos.ea == 2.0) ? r * r : exp(eos.ea * L));
+    rB = (eos.eb == 3.0) ? r * r * r : ((eos.eb == 2.0) ? r * r : exp(eos.eb * L));
+    rC = (eos.eg == 2.0) ? r * r : ((eos.eg == 1.0) ? r : exp(eos.eg * L));
+  } else {
+    rA = r; rB = r * r * r; rC = r * r;
+  }
+  s.rB = rB;
+  const double am1 = rA - 1.0;
+  s.uc1 = am1 * rA; s.uc2 = 0.0; s.Sp = 0.0;
+  const double W = eos.hb * rB * s.J;
+  s.W = W;
+  const double th_raw = e_int - W - eos.kA * am1 * am1;
+  if (th_raw != th_raw) s.bad = 1;
+  const double th_min = (eos.cvt0 * rC) * HS_LIT(th_clamp, 1e-6 - 1.0);
+  s.th = th_raw < th_min ? th_min : th_raw;
+  s.T = eos.t0 * fma(s.th, eos.inv_cvt0, rC);
+  s.e2 = -eos.hb * rB;
+  s.E3 = eos.kA1 * s.uc1 + eos.hg * s.th + eos.hbeta * W;
+  s.a = eos.c_a * (rB * s.I1);
+  const double m2r = -2.0 * rho, am = m2r * s.a, em = m2r * s.e2;   // sigma = -2 rho (a G - e2 G^2 + E3 I)
+  s.sig1[0] = fma(am, s.G[0], fma(-em, s.G2r1[0], m2r * s.E3));
+  s.sig1[1] = fma(am, s.G[1], -em * s.G2r1[1]);
+  s.sig1[2] = fma(am, s.G[2], -em * s.G2r1[2]);
+}
+
 // Physical x-flux of one phase in the 15-slot MPh order [0, den u1, mom(3), energy, A-block(9)].
 // HyperelasticityMPh.jl:168-172;  den*(u1 F_ij - u_i F_1j) == u1 A_ij - u_i A_1j.
 HS_HD void phase_flux(const PhaseState& s, const double* A, double* f) {

@@ -20,6 +20,19 @@ void hm_phase(const double* eos_abi, int gen, double alpha, const double* m, dou
   phase_acoustic_sym(e, s, out + k); k += 6;
   out[k++] = s.bad;
 }
+// row-1 flavour of phase_state (Cayley-Hamilton): out = rho, u(3), Etot, T, sig1(3), I1, J, G2r1(3), bad
+void hm_phase_row1(const double* eos_abi, int gen, double alpha, const double* m, double E, const double* A, double* out) {
+  EosDev e = make_eos_dev(*reinterpret_cast<const EosAbi*>(eos_abi));
+  PhaseState s;
+  if (gen) phase_state_row1<true>(e, alpha, m, E, A, s); else phase_state_row1<false>(e, alpha, m, E, A, s);
+  int k = 0;
+  out[k++] = s.rho; for (int i = 0; i < 3; ++i) out[k++] = s.u[i];
+  out[k++] = s.Etot; out[k++] = s.T;
+  for (int i = 0; i < 3; ++i) out[k++] = s.sig1[i];
+  out[k++] = s.I1; out[k++] = s.J;
+  for (int i = 0; i < 3; ++i) out[k++] = s.G2r1[i];
+  out[k++] = s.bad;
+}
 // symmetrised acoustic tensor for a general unit normal
 void hm_acoustic_n(const double* eos_abi, int gen, double alpha, const double* m, double E, const double* A, const double* n, double* S6) {
   EosDev e = make_eos_dev(*reinterpret_cast<const EosAbi*>(eos_abi));

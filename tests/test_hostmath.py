@@ -149,3 +149,37 @@ def test_hank2016_closed_forms_vs_dual_oracle(hm, oracle):
     out = np.zeros(1)
     assert hm.hm_hank_energy(_p(eos), 2.7, 1e9, _p(bad), _p(out)) == 1
     assert oracle.hank_energy(eos, 2.7, 1e9, bad)[1] == 1
+
+
+def test_row1_quadrature_state_matches_full_state(hm, oracle):
+    """phase_state_row1 (B = A A^T + Cayley-Hamilton; tuning build HS_PHASE_CH) against the full phase_state: everything the
+    non-conservative column reads (u, T, row 1 of sigma) to <= 5e-13, inside the 1e-12 per-evaluation budget."""
+    dp = C.POINTER(C.c_double)
+    hm.hm_phase_row1.argtypes = [dp, C.c_int, C.c_double, dp, C.c_double, dp, dp]
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for eos, gen in ((oracle.barton2009(), 0), (oracle.barton2009(), 1), (oracle.barton2009(c0=6.22, cv=9e-4, b0=3.16, beta=3.577, gamma=2.088), 1)):
+        for it in range(200):
+            alpha = rng.uniform(0.05, 0.95)
+            F = np.eye(3) + (0.3 if it % 4 == 0 else 0.1) * rng.uniform(-1, 1, (3, 3))
+            u = rng.uniform(-2, 2, 3); S = rng.uniform(0, 2e-3)
+            Pp = np.array([alpha, 8.9 / np.linalg.det(F), *u, S, *F.flatten(order="F")])
+            Q, _ = oracle.prim2cons([eos, eos], 1, np.concatenate([Pp, Pp]))
+            q = Q[:15]
+            m = np.ascontiguousarray(q[2:5]); A = np.ascontiguousarray(q[6:15])
+            full = np.zeros(64); r1 = np.zeros(32)
+            hm.hm_phase(_p(eos), gen, q[0], _p(m), q[5], _p(A), _p(full))
+            hm.hm_phase_row1(_p(eos), gen, q[0], _p(m), q[5], _p(A), _p(r1))
+            assert r1[14] == 0 and full[38] == 0
+            assert np.array_equal(r1[0:5], full[0:5])                       # rho, u, Etot: same expressions
+            sig_scale = max(np.abs(full[7:10]).max(), 1.0)
+            e_T = abs(r1[5] - full[6]) / abs(full[6]); e_s = np.abs(r1[6:9] - full[7:10]).max() / sig_scale
+            worst = max(worst, e_T, e_s)
+            assert e_T < 5e-13 and e_s < 5e-13, (e_T, e_s)   # (T carries the cancellation of e - W - U_cold: the full state holds 1e-12 vs the oracle)
+            # against the dual-number oracle as well
+            Po, _ = oracle.cons2prim([eos, eos], 1, Q); Po = Po[:15]
+            sig = oracle.stress(eos, Po[5], Po[6:15])
+            assert np.abs(r1[6:9] - sig[[0, 3, 6]]).max() < 1e-12 * max(np.abs(sig).max(), 1.0)
+            To = oracle.temperature(eos, Po[5], oracle.finger(Po[6:15]))
+            assert abs(r1[5] - To) < 1e-12 * abs(To)
+    print("row1 worst relative deviation", worst)
