@@ -28,7 +28,7 @@ namespace hs {
 #define HS_NODE_UNROLL 1
 #endif
 
-// single-phase: 1 = the step reads / writes the cached 1/rho + stress rows (aux rows 2..5), 0 = it recovers the
+// single-phase: 1 = the step reads / writes the cached 1/rho + stress rows (the aux rows after the wave-speed row(s)), 0 = it recovers the
 // state at its head instead (less traffic, more arithmetic) -- tuning knob
 #ifndef HS_SP_USE_CACHE
 #define HS_SP_USE_CACHE 1
@@ -73,7 +73,7 @@ __host__ __device__ constexpr int flux_row(int j) { return j - 1 - (j > 6) - (j 
 
 template <int MODEL> struct ModelTraits;
 // NAUX: cached per-cell rows next to the state.  Rows 0,1 = wave bounds lo / hi (all any consumer of
-// get_eigvals keeps).  The single-phase model also caches 1/rho and row 1 of the stress (rows 2..5):
+// get_eigvals keeps).  The single-phase model also caches 1/rho and row 1 of the stress (the rows after them):
 // the CFL sweep at the end of a step computes them anyway, and with them the next step's physical
 // flux needs no state recovery (saves ~20 % of the FP64 work for 32 B/cell more traffic each way).
 // HS_SP_CROW = 1: the single-phase model caches ONE wave-speed row, c_max, instead of the two bounds lo / hi = u1 -+ c_max
@@ -621,7 +621,7 @@ template <int T> constexpr size_t step_sp_smem_bytes() {
 // SINGLE: one problem (nprob == 1, every grid config): the problem index, the per-problem scalars, the column parities
 // and the 64-bit tile offsets are then loop invariants or 32-bit, and max(lambda) is flushed once per block.
 // TM2D: the state and the cached rows of a tile arrive as TWO tensor-map copies (13 x 128 and 6 x 128 doubles, any start
-// column, out-of-range columns zero-filled) issued by one thread, instead of 19 row copies spread over 20 lanes: ~40 fewer
+// column, out-of-range columns zero-filled) issued by one thread, instead of one row copy per state / cache row spread over 20 lanes: ~40 fewer
 // issue slots per warp and tile, no column parities, no thread-loaded last tile.  Needs an even stride (row pitch multiple of
 // 16 bytes) and a stride below 2^31; the host falls back to the row copies otherwise.
 template <int FLUX, bool GEN, int T, bool SINGLE, bool TM2D>
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     dst[3] = t;
     dst[4] = lam_cur;
   };
-  // 19 row copies per tile, spread over the four warps (a bulk copy is a uniform-datapath instruction: the lanes of a
+  // SP_NST row copies per tile, spread over the four warps (a bulk copy is a uniform-datapath instruction: the lanes of a
   // warp issue theirs one after the other, so one warp doing all 19 would reach the tile's barrier ~15 % late); the
   // window starts at the even element at or below the tile start.  Copies of the other warps may complete before thread
   // 0 has posted the expected byte count: the phase cannot complete before that arrival, and tx-count is signed.

@@ -93,7 +93,8 @@ int hs_advance(hs_ctx_t* ctx, int flux, double cfl, double dx, double t_end, int
 
 /* One step on HOST arrays: upload Qin, step, download into Qout (may alias Qin).  This is the
  * literal drop-in for one iteration of main.jl:202-227 with Q0 living in Julia memory;
- * host<->device copies are pipelined against the kernels. */
+ * the whole state crosses the host link once in each direction per call (the copies cannot overlap: dt needs
+ * max(lambda) of the complete uploaded state), so this form is bound by the link, not by the kernels. */
 int hs_step_host(hs_ctx_t* ctx, int flux, double cfl, double dx, const double* Qin, double* Qout,
                  double* dt_out);
 
