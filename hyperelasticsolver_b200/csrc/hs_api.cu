@@ -414,7 +414,16 @@ static int create_impl(hs_ctx_t** out, int model, const hs_barton2009_t* eos, in
     Part& p = c->parts[r];
     p.device = devices[r];
     if (slabs) {
-      p.a = ncells * r / ndev; p.b = ncells * (r + 1) / ndev;                  // same partition as slab.py::slab_bounds
+      // same partition as slab.py::slab_bounds: interior cuts are odd, so that every slab plus its halo cells is an even-sized
+      // array when ncells is even (an even row pitch is what the tensor-map tile copies of the single-phase step need)
+      auto cut = [&](int64_t k) -> int64_t {
+        if (k <= 0) return 0;
+        if (k >= ndev) return ncells;
+        int64_t x = ncells * k / ndev;
+        if (x % 2 == 0 && ncells / ndev >= 64) --x;
+        return x;
+      };
+      p.a = cut(r); p.b = cut(r + 1);
       p.lo_g = p.a - (r > 0 ? 1 : 0);
       const int64_t hi_g = p.b + (r < ndev - 1 ? 1 : 0);
       p.ghost = (r > 0 ? 1 : 0) | (r < ndev - 1 ? 2 : 0);

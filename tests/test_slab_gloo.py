@@ -55,12 +55,12 @@ def _worker(rank, world, port, model, flux, nx, nsteps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("model,flux", [(1, 1), (0, 1), (1, 0)])
-def test_two_rank_slab_matches_single_domain(model, flux):
+@pytest.mark.parametrize("model,flux,nx", [(1, 1, 41), (0, 1, 41), (1, 0, 41), (0, 1, 132)])   # 132: shifted (odd) interior cut
+def test_two_rank_slab_matches_single_domain(model, flux, nx):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    nx, nsteps = 41, 6
+    nsteps = 6
     procs = [ctx.Process(target=_worker, args=(r, 2, port, model, flux, nx, nsteps, q)) for r in range(2)]
     for p in procs: p.start()
     res = q.get(timeout=300)
@@ -74,11 +74,14 @@ def test_two_rank_slab_matches_single_domain(model, flux):
 
 def test_slab_bounds_cover_domain():
     from hyperelasticsolver_b200.slab import slab_bounds
-    for n, w in [(41, 2), (1000, 8), (1 << 20, 4), (17, 5)]:
+    for n, w in [(41, 2), (1000, 8), (1 << 20, 4), (17, 5), (1 << 25, 2), (1 << 27, 8), (1 << 28, 8), (1 << 28, 1), (130, 2)]:
         prev = 0
         for r in range(w):
             a, b, lo, hi = slab_bounds(n, w, r)
             assert a == prev and b > a
             assert lo == a - (r > 0) and hi == b + (r < w - 1)
+            assert abs((b - a) - n / w) <= 2            # balanced to within a cell or two
+            if n % 2 == 0 and n // w >= 64:
+                assert (hi - lo) % 2 == 0                # even local arrays: the tensor-map tile copies apply on every rank
             prev = b
         assert prev == n
