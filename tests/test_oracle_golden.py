@@ -206,3 +206,65 @@ def test_hank2016_against_pyoracle_vectors(oracle):
         assert st == 0 and abs(p - c["pressure"]) <= 1e-12 * eos[2] * eos[3]
         s_, st = oracle.hank_stress(eos, c["den"], c["pres"], np.array(c["distortion"]))
         assert st == 0 and np.abs(s_ - np.array(c["stress"])).max() <= 1e-12 * np.abs(c["stress"]).max()
+
+
+def _random_mph_states(oracle, rng, n, eos=None):
+    P = []
+    for _ in range(n):
+        a1 = rng.uniform(0.1, 0.9); row = []
+        for a in (a1, 1 - a1):
+            F = np.eye(3) + 0.1 * rng.uniform(-1, 1, (3, 3))
+            row += [a, 8.9 / np.linalg.det(F), *rng.uniform(-1, 1, 3), rng.uniform(0, 1e-3), *F.flatten(order="F")]
+        P.append(row)
+    Q, st = oracle.prim2cons(eos, 1, np.array(P))
+    assert st == 0
+    return Q
+
+
+def test_numerical_flux_consistency(oracle):
+    """Properties every consistent path-conservative flux has, independent of any golden number (NumFluxes.jl:25-132):
+    equal states give no fluctuation and (LxF) the physical flux; D- + D+ of LxF is the whole path integral; swapping the
+    two phases of both states swaps the two halves of every output."""
+    rng = np.random.default_rng(21)
+    Q = _random_mph_states(oracle, rng, 6)
+    eig, _ = oracle.get_eigvals(None, 1, Q)
+    F, _ = oracle.flux(None, 1, Q)
+    cons, dm, dp, s, st = oracle.hll(None, Q, Q, eig, eig)
+    assert st == 0 and np.all(cons == 0.0)
+    assert np.abs(dm).max() < 1e-12 * np.abs(F).max() and np.abs(dp).max() < 1e-12 * np.abs(F).max()
+    lam = 7.0
+    cons, dm, dp, st = oracle.lxf(None, Q, Q, lam)
+    assert np.abs(cons - F).max() < 1e-13 * np.abs(F).max() and np.all(dm == 0.0) and np.all(dp == 0.0)
+    Ql, Qr = Q[:3], Q[3:]
+    cons, dm, dp, st = oracle.lxf(None, Ql, Qr, lam)
+    Fl, Fr = F[:3], F[3:]
+    assert np.abs(cons - (0.5 * (Fl + Fr) - 0.5 * lam * (Qr - Ql))).max() < 1e-13 * np.abs(F).max()
+    assert np.array_equal(dm, dp)                                                    # NumFluxes.jl:50-51
+    # phase-swap symmetry (k = (1/2, 1/2), omega = 0: nothing distinguishes the phases, HyperelasticityMPh.jl:205-217)
+    sw = lambda X: np.concatenate([X[..., 15:], X[..., :15]], axis=-1)
+    swe = lambda E: np.concatenate([E[..., 6:], E[..., :6]], axis=-1)
+    c1, m1, p1, s1, _ = oracle.hll(None, Ql, Qr, eig[:3], eig[3:])
+    c2, m2, p2, s2, _ = oracle.hll(None, sw(Ql), sw(Qr), swe(eig[:3]), swe(eig[3:]))
+    scale = np.abs(m1).max()
+    assert np.abs(sw(m2) - m1).max() < 1e-13 * scale and np.abs(sw(p2) - p1).max() < 1e-13 * scale and np.array_equal(s1, s2)
+
+
+def test_wave_speeds_rotate_with_the_frame(oracle):
+    """get_eigvals for a unit normal n (HyperelasticityMPh.jl:252-266, EquationsOfState.jl:223) equals get_eigvals for
+    (1,0,0) of the state seen from a frame rotated by R with R n = e1: u -> R u, F -> R F (objectivity)."""
+    rng = np.random.default_rng(23)
+    Q = _random_mph_states(oracle, rng, 8)
+    for k in range(8):
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        a = np.cross(n, [1.0, 0.0, 0.0]) if abs(n[0]) < 0.9 else np.cross(n, [0.0, 1.0, 0.0])
+        a /= np.linalg.norm(a)
+        R = np.stack([n, a, np.cross(n, a)])                                          # rows: R n = e1, orthonormal
+        assert np.allclose(R @ n, [1, 0, 0]) and np.allclose(R @ R.T, np.eye(3))
+        q = Q[k].copy(); qr = q.copy()
+        for p in (0, 15):
+            qr[p + 2:p + 5] = R @ q[p + 2:p + 5]
+            qr[p + 6:p + 15] = (R @ q[p + 6:p + 15].reshape(3, 3, order="F")).flatten(order="F")
+        en, st = oracle.get_eigvals_n(None, q[None], n)
+        e1, st1 = oracle.get_eigvals(None, 1, qr[None])
+        assert st == 0 and st1 == 0
+        assert np.abs(en - e1).max() < 1e-12 * np.abs(e1).max()
