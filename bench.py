@@ -367,7 +367,9 @@ def run_ours(args):
         import oracle as O
         threads = O.hardware_threads()
         v, sample, el = cpu_oracle_rate(model, args.cpu_seconds, threads, literal=True)
+        v1, sample1, el1 = cpu_oracle_rate(model, min(4.0, args.cpu_seconds), 1, literal=True)   # also single-thread
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "seconds": el,
+               "single_thread": {"value": v1, "sample": sample1, "seconds": el1},
                "note": "C++ restatement of main.jl (dual-number AD like ForwardDiff); Julia itself is not installed in this image"}
 
     if rank == 0:
