@@ -75,11 +75,13 @@ constexpr int T_STEP_MPH = HS_T_STEP_MPH, T_STEP_SP = HS_T_STEP_SP, T_FACE = 64;
 
 template <int MODEL, int FLUX, bool GEN, int T, bool SAME>
 int launch_step_s(const StepArgs& a, int64_t nblocks, cudaStream_t st) {
-  static bool attr_set = false;
   constexpr size_t smem = step_smem_bytes<MODEL, T>();
-  if (!attr_set) {
+  static std::atomic<unsigned> attr_dev_mask{0};   // (the attribute is per device and per kernel instantiation)
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (!(attr_dev_mask.load() & (1u << (dev & 31)))) {
     CU(cudaFuncSetAttribute(k_step<MODEL, FLUX, GEN, T, SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_dev_mask.fetch_or(1u << (dev & 31));
   }
   k_step<MODEL, FLUX, GEN, T, SAME><<<(unsigned)nblocks, T, smem, st>>>(a);
   g_launches++;
@@ -135,12 +137,12 @@ bool make_tile_map(CUtensorMap* m, const double* base, long long stride, int row
 template <int FLUX, bool GEN, int T, bool SINGLE, bool TM2D>
 int launch_step_sp_s(const StepArgs& a, int64_t ntiles, int kper, const CUtensorMap& mq, const CUtensorMap& ma, cudaStream_t st) {
   constexpr size_t smem = step_sp_smem_bytes<T>();
-  static int attr_dev_mask = 0;   // (the attribute is per device and per kernel instantiation)
+  static std::atomic<unsigned> attr_dev_mask{0};   // (the attribute is per device and per kernel instantiation)
   int dev = 0;
   CU(cudaGetDevice(&dev));
-  if (!(attr_dev_mask & (1 << (dev & 31)))) {
+  if (!(attr_dev_mask.load() & (1u << (dev & 31)))) {
     CU(cudaFuncSetAttribute(k_step_sp<FLUX, GEN, T, SINGLE, TM2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_dev_mask |= 1 << (dev & 31);
+    attr_dev_mask.fetch_or(1u << (dev & 31));
   }
   const int64_t nblocks = (ntiles + kper - 1) / kper;
   k_step_sp<FLUX, GEN, T, SINGLE, TM2D><<<(unsigned)nblocks, T, smem, st>>>(a, kper, mq, ma);
@@ -299,6 +301,8 @@ int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_e
   a.cur = (int)(n % 3); a.nxt = (int)((n + 1) % 3); a.clr = (int)((n + 2) % 3);
   a.ghost = ghost_mask;
   a.cfl = cfl; a.dx = dx; a.t_end = t_end;
+  static const unsigned long long spin_ns = 1000000000ull * (unsigned long long)(std::getenv("HS_TMA_TIMEOUT_S") ? std::atoi(std::getenv("HS_TMA_TIMEOUT_S")) : 10);
+  a.spin_ns = spin_ns;
   a.eos = eos_pair(p);
   if (p->model == HS_MODEL_MPH30) {
     constexpr int T = T_STEP_MPH, CPB = T / 2;

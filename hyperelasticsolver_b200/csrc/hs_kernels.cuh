@@ -312,6 +312,7 @@ struct StepArgs {
   int cur, nxt, clr;
   int ghost;                 // bit 0 / 1: the first / last cell is a halo copy owned by a neighbouring slab
   double cfl, dx, t_end;
+  unsigned long long spin_ns;   // time limit of the tile-copy wait of k_step_sp (never hang the GPU on a lost copy)
   EosPair eos;
 };
 
@@ -568,6 +569,12 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
 // Tiles whose 130-element window would run past the end of the arrays (the last one or two of the
 // launch) are loaded by the threads themselves.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 namespace tma {
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -739,11 +746,15 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     // (row copies: stage row = slot - 2, column shifted by the row's parity; tensor-map copies: stage row = variable, no shift)
 #define SQ(j, col) st[(TM2D ? sp_var(j) : (j) - 2) * TS + (col) + (TM2D ? 0 : ((sp_var(j) & 1) ? po : pe))]
 #define SA(r, col) st[(13 + (r)) * TS + (col) + (TM2D ? 0 : (((r) & 1) ? po : pe))]
+    bool lost = false;   // the tile copy did not arrive in time: flag it and write NOTHING of this tile (the input buffer stays intact)
     if (cur_tma) {
       const unsigned par = (phase_bits >> s) & 1u;
-      unsigned spins = 0;
-      while (!tma::mbar_try_wait(&mbar[s], par)) {
-        if (++spins > (1u << 20)) { atomicOr(g.status, 4); break; }   // never hang the GPU on a lost copy
+      if (!tma::mbar_try_wait(&mbar[s], par)) {
+        // wall-clock limit (%globaltimer, several seconds: time-slicing, MPS, a debugger or the sanitizer cannot trip it)
+        const unsigned long long t0 = global_timer_ns();
+        while (!tma::mbar_try_wait(&mbar[s], par)) {
+          if (global_timer_ns() - t0 > g.spin_ns) { atomicOr(g.status, 4); lost = true; break; }
+        }
       }
       phase_bits ^= 1u << s;
     } else {
@@ -754,9 +765,9 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       __syncthreads();
     }
 
-    const bool own_interior = valid && tid >= 1 && tid <= T - 2 && c <= g.ncells - 2;
+    const bool own_interior = valid && !lost && tid >= 1 && tid <= T - 2 && c <= g.ncells - 2;
     // frozen physical boundary cells, main.jl:219-220 (halo cells of a slab belong to the neighbour)
-    const bool own_frozen = valid && ((c == 0 && !(g.ghost & 1)) || (c == g.ncells - 1 && !(g.ghost & 2)));
+    const bool own_frozen = valid && !lost && ((c == 0 && !(g.ghost & 1)) || (c == g.ncells - 1 && !(g.ghost & 2)));
     const double dt = scv[0], upd = scv[1], lambda = scv[2], t_cur = scv[3];
     const bool active = t_cur < g.t_end;                  // while t < T, main.jl:202
     (void)lambda;
@@ -1043,12 +1054,6 @@ __global__ void k_halo(double* Q, double* aux, double* left, double* right, long
 constexpr int MBOX_MAXW = 40, MBOX_MAXR = 8;
 constexpr int MBOX_STRIDE = 2 * MBOX_MAXW + 2 * MBOX_MAXR;    // doubles per parity
 struct PeerPtrs { double* p[MBOX_MAXR]; };
-
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
 
 __global__ void __launch_bounds__(64) k_exchange_p2p(double* Q, double* aux, unsigned long long* lam_slot, const PeerPtrs peers,
                                                      long long stride, int ncells, int nvar, int naux, int rank, int world,

@@ -38,8 +38,8 @@ namespace hs {
 // a register pair with two moves at every use (it will not keep them live at 128 registers).  As constant-bank
 // operands they cost nothing.
 #ifdef __CUDACC__
-struct HotLits { double third, sixth, th_clamp, tiny, r_hi, r_lo, mu0, mu1, mu2, mu3; };
-__constant__ HotLits c_lit = {1.0 / 3.0, 1.0 / 6.0, 1e-6 - 1.0, 1e-280, 1.0000001, -0.875,
+struct HotLits { double third, sixth, th_clamp, sp_clamp, tiny, r_hi, r_lo, mu0, mu1, mu2, mu3; };
+__constant__ HotLits c_lit = {1.0 / 3.0, 1.0 / 6.0, 1e-6 - 1.0, 1e-6, 1e-280, 1.0000001, -0.875,
                               1.7464452327513027, 0.32800957660022223, -0.1425897443947186, 0.08116787571408166};
 #endif
 #ifdef __CUDA_ARCH__
@@ -55,7 +55,7 @@ struct EosAbi {
 // ... and the derived constants the kernels use (computed once on the host).
 struct EosDev {
   double rho0, inv_rho0, cvt0, inv_cvt0, t0, cv;
-  double b0sq, hb;        // b0^2, b0^2/2
+  double t0c, hb;         // t0 * 1e-6 (temperature factor of a clamped state), b0^2/2
   double kA, kA1;         // k0/(2 alpha^2), k0/(2 alpha)
   double ea, eb, eg;      // alpha, beta, gamma
   double hbeta, hg;       // beta/2, gamma/2
@@ -71,7 +71,7 @@ inline EosDev make_eos_dev(const EosAbi& e) {
   d.rho0 = e.rho0; d.inv_rho0 = 1.0 / e.rho0;
   d.cvt0 = e.cv * e.t0; d.inv_cvt0 = 1.0 / (e.cv * e.t0);
   d.t0 = e.t0; d.cv = e.cv;
-  d.b0sq = e.b0sq; d.hb = 0.5 * e.b0sq;
+  d.t0c = e.t0 * 1e-6; d.hb = 0.5 * e.b0sq;
   d.kA = 0.5 * e.k0 / (e.alpha * e.alpha); d.kA1 = 0.5 * e.k0 / e.alpha;
   d.ea = e.alpha; d.eb = e.beta; d.eg = e.gamma;
   d.hbeta = 0.5 * e.beta; d.hg = 0.5 * e.gamma;
@@ -221,9 +221,13 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   if (th_raw != th_raw) s.bad = 1;
   const double cr = eos.cvt0 * rC;
   const double th_min = cr * HS_LIT(th_clamp, 1e-6 - 1.0);
-  s.th = th_raw < th_min ? th_min : th_raw;
-  s.T = eos.t0 * fma(s.th, eos.inv_cvt0, rC);
-  s.Sp = fma(s.th * eos.inv_cvt0, irC, 1.0);
+  // Clamped branch (EquationsOfState.jl:152-154, S' = 1e-6): S' and T = t0 I3^(gamma/2) S' are SELECTED, never formed
+  // through the sums below -- with th = th_min those cancel six digits (T off by ~3e-10 against the reference's
+  // exp(log(1e-6))).
+  const bool clamped = th_raw < th_min;
+  s.th = clamped ? th_min : th_raw;
+  s.T = clamped ? eos.t0c * rC : eos.t0 * fma(th_raw, eos.inv_cvt0, rC);
+  s.Sp = clamped ? HS_LIT(sp_clamp, 1e-6) : fma(th_raw * eos.inv_cvt0, irC, 1.0);
   // first derivatives of e(I1,I2,I3;S):  e1 = b0^2 rB I1/3, e2 = -b0^2 rB/2, E3 = e3*I3 (its shear part is (beta/2) W);
   // a = e1 + e2 I1 = -(b0^2/6) rB I1
   s.e2 = -eos.hb * rB;
@@ -290,8 +294,9 @@ HS_HD void phase_state_row1(const EosDev& eos, double alpha, const double* m, do
   const double th_raw = e_int - W - eos.kA * am1 * am1;
   if (th_raw != th_raw) s.bad = 1;
   const double th_min = (eos.cvt0 * rC) * HS_LIT(th_clamp, 1e-6 - 1.0);
-  s.th = th_raw < th_min ? th_min : th_raw;
-  s.T = eos.t0 * fma(s.th, eos.inv_cvt0, rC);
+  const bool clamped = th_raw < th_min;        // (same selection as phase_state)
+  s.th = clamped ? th_min : th_raw;
+  s.T = clamped ? eos.t0c * rC : eos.t0 * fma(th_raw, eos.inv_cvt0, rC);
   s.e2 = -eos.hb * rB;
   s.E3 = eos.kA1 * s.uc1 + eos.hg * s.th + eos.hbeta * W;
   s.a = eos.c_a * (rB * s.I1);

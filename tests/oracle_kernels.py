@@ -14,7 +14,12 @@ class OracleKernels:
     def __init__(self, eos_blocks, model):
         self.model = model
         self.nvar = O.NVAR[model]
-        self.naux = 6 if model == O.SP13 else 2   # rows 0,1 = lo, hi; the rest is carried but unused by the double
+        # same number of cached rows as the product layout (hsd_naux of the library as built), so halo buffers and
+        # mailboxes have the product's width; the double keeps lo / hi in rows 0, 1 and carries the rest unused
+        from hyperelasticsolver_b200 import _lib as L
+        L.lib()
+        self.naux = L.NAUX[model]
+        assert self.naux >= 2
         self.neig = O.NEIG[model]
         self.eos = eos_blocks
         self.device = torch.device("cpu")

@@ -183,3 +183,72 @@ def test_row1_quadrature_state_matches_full_state(hm, oracle):
             To = oracle.temperature(eos, Po[5], oracle.finger(Po[6:15]))
             assert abs(r1[5] - To) < 1e-12 * abs(To)
     print("row1 worst relative deviation", worst)
+
+
+def test_entropy_clamp_branch(hm, oracle):
+    """EquationsOfState.jl:152-154: e_int below the cold curve -> S' = 1e-6 exactly.  The kernels select
+    S' and T = t0 I3^(gamma/2) S' in that branch instead of forming them through 1 + th/(cv t0 I3^(gamma/2)), which cancels
+    six digits.  Also low-entropy UNclamped states: there S' = 1 + th_raw/(...) is ill-conditioned in the reference itself
+    (the reference's own roundoff in e_int = E - |u|^2/2 is amplified by 1/(cv T)), so agreement is asserted at that
+    conditioning bound, not at 1e-12."""
+    rng = np.random.default_rng(7)
+    eos = oracle.barton2009()
+    rel = lambda a, b, s=None: np.abs(np.asarray(a) - np.asarray(b)).max() / (np.abs(np.asarray(b)).max() if s is None else s)
+    n_clamped = 0
+    for it in range(200):
+        alpha = rng.uniform(0.05, 0.95)
+        F = np.eye(3) + 0.1 * rng.uniform(-1, 1, (3, 3))
+        u = rng.uniform(-2, 2, 3); S = rng.uniform(0, 4e-4)
+        Pp = np.array([alpha, 8.9 / np.linalg.det(F), *u, S, *F.flatten(order="F")])
+        Q, _ = oracle.prim2cons([eos, eos], 1, np.concatenate([Pp, Pp]))
+        Q = Q.copy()
+        Q[5] -= Q[1] * rng.uniform(0.4, 2.0)       # push the internal energy below the cold curve
+        Q[20] = Q[5] * Q[15] / Q[0]                # (second phase: same state, its own alpha)
+        assert np.isclose(Q[1] / Q[0], Q[16] / Q[15])
+        q = Q[:15]
+        out = np.zeros(64)
+        m = np.ascontiguousarray(q[2:5]); A = np.ascontiguousarray(q[6:15])
+        hm.hm_phase(_p(eos), 0, q[0], _p(m), q[5], _p(A), _p(out))
+        Sp, T, sig1, cmax, fl, S6, bad = out[5], out[6], out[7:10], out[16], out[17:32], out[32:38], out[38]
+        Po, _ = oracle.cons2prim([eos, eos], 1, Q); Po = Po[:15]
+        Fo, So = Po[6:15], Po[5]
+        Go = oracle.finger(Fo)
+        if not np.isclose(So, eos[2] * np.log(1e-6), rtol=1e-12):
+            continue
+        n_clamped += 1
+        assert bad == 0
+        assert Sp == 1e-6                                           # selected, not computed
+        assert rel(T, oracle.temperature(eos, So, Go)) < 1e-13
+        assert rel(sig1, oracle.stress(eos, So, Fo)[[0, 3, 6]]) < 1e-12
+        fo, _ = oracle.flux([eos, eos], 1, Q)
+        assert rel(fl, fo[:15]) < 1e-12
+        ac = oracle.acoustic(eos, So, Fo)
+        assert rel(S6, [ac[0, 0], ac[0, 1], ac[0, 2], ac[1, 1], ac[1, 2], ac[2, 2]]) < 1e-12
+        eg, _ = oracle.get_eigvals([eos, eos], 1, Q)
+        assert rel(Po[2] + cmax, eg[0].max()) < 1e-13
+    assert n_clamped >= 150
+    # low-entropy states that are NOT clamped (S' between 1e-5 and 1e-2)
+    worst = 0.0
+    for it in range(200):
+        alpha = rng.uniform(0.05, 0.95)
+        F = np.eye(3) + 0.1 * rng.uniform(-1, 1, (3, 3))
+        u = rng.uniform(-2, 2, 3)
+        Sprime = 10.0 ** rng.uniform(-5, -2)
+        Pp = np.array([alpha, 8.9 / np.linalg.det(F), *u, eos[2] * np.log(Sprime), *F.flatten(order="F")])
+        Q, _ = oracle.prim2cons([eos, eos], 1, np.concatenate([Pp, Pp]))
+        q = Q[:15]
+        out = np.zeros(64)
+        m = np.ascontiguousarray(q[2:5]); A = np.ascontiguousarray(q[6:15])
+        hm.hm_phase(_p(eos), 0, q[0], _p(m), q[5], _p(A), _p(out))
+        Po, _ = oracle.cons2prim([eos, eos], 1, Q); Po = Po[:15]
+        Go = oracle.finger(Po[6:15])
+        To = oracle.temperature(eos, Po[5], Go)
+        # T = (e_int - W - U_cold)/cv + t0 I3^(gamma/2): roundoff eps (|E| + |u|^2/2) of e_int = E - |u|^2/2 shows up as
+        # eps (|E| + |u|^2/2)/(cv T) relative in T -- in the reference's own arithmetic as much as in the kernels'
+        cond = (abs(q[5] / q[1]) + 0.5 * (Po[2:5] ** 2).sum()) / (eos[2] * To)
+        worst = max(worst, abs(out[6] - To) / To / (cond * 2.2e-16))
+        assert abs(out[6] - To) / To < 64 * 2.2e-16 * max(cond, 1.0)
+        # everything that does not divide by S' stays at 1e-12
+        assert rel(out[7:10], oracle.stress(eos, Po[5], Po[6:15])[[0, 3, 6]]) < 1e-12
+    assert worst < 64, worst
+    print('worst T error in units of eps * cond:', worst)
