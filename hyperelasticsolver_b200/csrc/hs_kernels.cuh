@@ -178,10 +178,11 @@ __device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const d
 //   FROM_END = false: psi(s) = base + s d          (base = start of the segment)
 //   FROM_END = true : psi(s) = base - (1 - s) d    (base = end of the segment)
 // i.e. one fused multiply-add per component instead of the two of Q_l (1-s) + Q_r s.  MPh only.
-// HS_PHASE_CH = 1 (tuning build, not yet measured on a GPU): quadrature states through phase_state_row1
-// (B = A A^T + Cayley-Hamilton, hs_phase.cuh) -- ~10 FP64 instructions fewer per state, results differ by a few ulp.
+// HS_PHASE_CH = 1 (default since round 2: 1.642 vs 1.591 G cell-updates/s on the same box, GPU parity suite green): quadrature
+// states through phase_state_row1 (B = A A^T + Cayley-Hamilton, hs_phase.cuh) -- ~10 FP64 instructions fewer per state, results
+// differ by a few ulp.  0 = the full phase_state.
 #ifndef HS_PHASE_CH
-#define HS_PHASE_CH 0
+#define HS_PHASE_CH 1
 #endif
 template <bool GEN, int T, bool FROM_END>
 __device__ __forceinline__ void path_integral(const EosDev& eos, const double* base, const double* d, const double* xs,

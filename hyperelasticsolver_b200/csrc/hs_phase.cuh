@@ -239,8 +239,7 @@ HS_HD void phase_state(const EosDev& eos, double alpha, const double* m, double 
   s.sig1[2] = fma(am, G[2], -em * s.G2r1[2]);
 }
 
-// Row-1 flavour of phase_state for the quadrature states of the path integrals (tuning build HS_PHASE_CH, not yet measured on a
-// GPU; the default build does not use it).  The non-conservative column only needs u, T and row 1 of sigma, i.e. row 1 of G and
+// Row-1 flavour of phase_state for the quadrature states of the path integrals (HS_PHASE_CH, the default since round 2).  The non-conservative column only needs u, T and row 1 of sigma, i.e. row 1 of G and
 // of G^2, tr G and J.  They come from B = A A^T without forming G:  G = kappa^2 cof(B) (row 1 and the diagonal of the cofactor
 // matrix only), G^-1 = B / den^2, I2 = I3 tr(G^-1) with I3 / den^2 = 1/(alpha rho0)^2, and by Cayley-Hamilton
 // G^2 = I1 G - I2 1 + I3 G^-1: about 10 FP64 instructions fewer per state for a few ulp of cancellation in G^2
