@@ -213,7 +213,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     O.run(eos, om, O.HLL, riemann_grid(Qlr[0], Qlr[1], probe), 0.6, 1.0 / probe, 1e9, 1, nthreads=threads, literal=True)
     rate = probe / (time.perf_counter() - t0)
-    cells = int(min(1 << 20, max(2048, rate * 90.0 / (args.steps + args.warmup))))
+    cells = int(min(1 << 20, max(2048, rate * args.ref_seconds / (args.steps + args.warmup))))
     Q = riemann_grid(Qlr[0], Qlr[1], cells)
     if args.warmup:
         Q = O.run(eos, om, O.HLL, Q, 0.6, 1.0 / cells, 1e9, args.warmup, nthreads=threads, literal=True)["Q"]
@@ -575,6 +575,7 @@ def main():
                     help="default: sp13_2p24 on one GPU, sp13_2p28 (strong) on several, plus the other BASELINE configs as sub-results")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=90.0, help="--impl reference: CPU work the bounded sample is sized for")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-subconfigs", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")

@@ -79,6 +79,9 @@ SIGNATURES = {
     "hs_step": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp]),
     "hs_advance": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, _i64, _vp, _vp, _vp]),
     "hs_step_host": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "hs_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "hs_host_unregister": (C.c_int, [_vp]),
+    "hs_step_host_stats": (C.c_int, [_vp, _ip, _ip]),
     "hs_cons2prim": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),
     "hs_prim2cons": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),
     "hs_flux": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),

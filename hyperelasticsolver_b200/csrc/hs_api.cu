@@ -115,10 +115,12 @@ EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-bool make_tile_map(CUtensorMap* m, const double* base, long long stride, int rows) {
+// width: columns that exist from `base` on (the whole array, or a window of it when the step runs on a sub-range of the cells:
+// then base points into the array and the rows are still `stride` doubles apart); columns >= width are zero-filled.
+bool make_tile_map(CUtensorMap* m, const double* base, long long width, long long stride, int rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)stride, (cuuint64_t)rows};
+  const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(double)};
   const cuuint32_t box[2] = {128u, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1u, 1u};
@@ -161,7 +163,8 @@ int launch_step_sp(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st)
   CUtensorMap mq, ma;
   std::memset(&mq, 0, sizeof mq); std::memset(&ma, 0, sizeof ma);
   const bool tm2d = !(e2 && e2[0] == '0') && (a.stride % 2 == 0) && a.stride < 0x7fffffffLL &&
-                    make_tile_map(&mq, a.Qin, a.stride, 13) && make_tile_map(&ma, a.aux_in, a.stride, SP_NAX);
+                    make_tile_map(&mq, a.Qin, (long long)a.ncells * a.nprob, a.stride, 13) &&
+                    make_tile_map(&ma, a.aux_in, (long long)a.ncells * a.nprob, a.stride, SP_NAX);
   if (tm2d) {
     if (single) return launch_step_sp_s<FLUX, GEN, T, true, true>(a, ntiles, kper, mq, ma, st);
     return launch_step_sp_s<FLUX, GEN, T, false, true>(a, ntiles, kper, mq, ma, st);
@@ -238,33 +241,36 @@ int hsd_problem_init(hsd_problem_t* p, int model, const hs_barton2009_t* eos, in
   return HS_OK;
 }
 
-int hsd_aos_to_soa(const hsd_problem_t* p, const double* aos, double* soa, void* stream) {
-  const long long n = p->stride;
+// n cells starting at aos / soa (which may point into larger arrays), rows of the SoA array `stride` doubles apart
+static int transpose_range(int model, bool to_soa, const double* src, double* dst, long long n, long long stride, cudaStream_t st) {
   constexpr int TC = 64;
   const unsigned nb = (unsigned)((n + TC - 1) / TC);
-  if (p->model == HS_MODEL_MPH30) k_aos_to_soa<30, TC><<<nb, 256, 0, (cudaStream_t)stream>>>(aos, soa, n, p->stride);
-  else k_aos_to_soa<13, TC><<<nb, 256, 0, (cudaStream_t)stream>>>(aos, soa, n, p->stride);
+  if (to_soa) {
+    if (model == HS_MODEL_MPH30) k_aos_to_soa<30, TC><<<nb, 256, 0, st>>>(src, dst, n, stride);
+    else k_aos_to_soa<13, TC><<<nb, 256, 0, st>>>(src, dst, n, stride);
+  } else {
+    if (model == HS_MODEL_MPH30) k_soa_to_aos<30, TC><<<nb, 256, 0, st>>>(src, dst, n, stride);
+    else k_soa_to_aos<13, TC><<<nb, 256, 0, st>>>(src, dst, n, stride);
+  }
   g_launches++;
   CU(cudaGetLastError());
   return HS_OK;
+}
+
+int hsd_aos_to_soa(const hsd_problem_t* p, const double* aos, double* soa, void* stream) {
+  return transpose_range(p->model, true, aos, soa, p->stride, p->stride, (cudaStream_t)stream);
 }
 
 int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa, double* aos, void* stream) {
-  const long long n = p->stride;
-  constexpr int TC = 64;
-  const unsigned nb = (unsigned)((n + TC - 1) / TC);
-  if (p->model == HS_MODEL_MPH30) k_soa_to_aos<30, TC><<<nb, 256, 0, (cudaStream_t)stream>>>(soa, aos, n, p->stride);
-  else k_soa_to_aos<13, TC><<<nb, 256, 0, (cudaStream_t)stream>>>(soa, aos, n, p->stride);
-  g_launches++;
-  CU(cudaGetLastError());
-  return HS_OK;
+  return transpose_range(p->model, false, soa, aos, p->stride, p->stride, (cudaStream_t)stream);
 }
 
+// accumulate: keep the slot's current value and max into it (the sweep of one window of a grid that arrives chunk by chunk)
 static int wave_bounds_impl(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot,
-                            double* eig_full, cudaStream_t st) {
+                            double* eig_full, cudaStream_t st, bool accumulate = false) {
   if (slot < 0 || slot > 2) return fail(HS_ERR_ARG, "slot must be 0..2");
   unsigned long long* lam = scal_lam(scal) + (size_t)slot * p->nprob;
-  CU(cudaMemsetAsync(lam, 0, sizeof(double) * p->nprob, st));
+  if (!accumulate) CU(cudaMemsetAsync(lam, 0, sizeof(double) * p->nprob, st));
   int* status = scal_status(scal, p->nprob);
   const EosPair e = eos_pair(p);
   constexpr int T = 128;
@@ -374,6 +380,11 @@ struct Part {                 // one slab (or one share of an ensemble) on one d
   double* mbox = nullptr;     // exchange mailbox (slab mode only)
   double* dt_hist = nullptr;  // grown on demand
   int64_t hist_cap = 0;
+  // chunk-pipelined host step (hs_step_host): copy streams, output staging, the sweep's own scalar block, per-chunk events
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  double* stage_out = nullptr;
+  double* scal_sweep = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_out;
 };
 }  // namespace
 
@@ -385,6 +396,8 @@ struct hs_ctx {
   std::vector<void*> mailboxes;
   int64_t n = 0;              // launch counter since the last upload (selects buffers and scalar slots)
   uint64_t xseq = 0;          // exchange sequence number (never reused)
+  bool has_state = false;     // the device holds a state with a valid max(lambda) slot (after upload / step / step_host)
+  int64_t pipelined_calls = 0, speculation_hits = 0;   // hs_step_host bookkeeping (hs_step_host_stats)
   // host range (in cells / in problems) a part reads and writes
   int64_t first_cell(const Part& p) const { return slabs ? p.lo_g : p.a * ncells; }
   int64_t owned_first(const Part& p) const { return slabs ? p.a : p.a * ncells; }
@@ -484,7 +497,11 @@ int hs_destroy(hs_ctx_t* c) {
   for (auto& p : c->parts) {
     DeviceGuard g(p.device);
     for (int k = 0; k < 2; ++k) { cudaFree(p.Q[k]); cudaFree(p.aux[k]); }
-    cudaFree(p.scal); cudaFree(p.stage); cudaFree(p.mbox); cudaFree(p.dt_hist);
+    cudaFree(p.scal); cudaFree(p.stage); cudaFree(p.mbox); cudaFree(p.dt_hist); cudaFree(p.stage_out); cudaFree(p.scal_sweep);
+    for (auto e : p.ev_in) cudaEventDestroy(e);
+    for (auto e : p.ev_out) cudaEventDestroy(e);
+    if (p.s_h2d) cudaStreamDestroy(p.s_h2d);
+    if (p.s_d2h) cudaStreamDestroy(p.s_d2h);
     if (p.stream) cudaStreamDestroy(p.stream);
   }
   delete c;
@@ -544,6 +561,7 @@ int hs_upload(hs_ctx_t* c, const double* Q) {
       CU(cudaStreamSynchronize(p.stream));
     }
   }
+  c->has_state = true;
   return read_status(c);
 }
 
@@ -702,11 +720,208 @@ int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64
   return read_status(c);
 }
 
-int hs_step_host(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin, double* Qout, double* dt_out) {
+static int step_host_plain(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin, double* Qout, double* dt_out) {
   int rc = hs_upload(c, Qin); if (rc && rc != HS_ERR_DOMAIN) return rc;
   int rc2 = hs_step(c, flux, cfl, dx, dt_out); if (rc2 && rc2 != HS_ERR_DOMAIN) return rc2;
   int rc3 = hs_download(c, Qout); if (rc3) return rc3;
   return rc ? rc : rc2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chunk-pipelined host step (one grid on one device).
+//
+// A host-resident step is H2D(Q0) -> CFL sweep -> step -> D2H(Q1), and dt = cfl dx / max(lambda) needs the sweep of the WHOLE
+// uploaded state before any cell can be updated, so the two copies cannot overlap: 2 x state / link bandwidth per step.  In a
+// solver loop, however, the state passed in is the state the previous call returned, whose max(lambda) the previous fused step
+// already produced (it sits in the context's scalar slot).  That value is used as a HINT:
+//   for chunk i of the grid (even boundaries b_i, so that every window below is an even-sized array starting on an even cell --
+//   what the tensor-map tile copies need):
+//     copy stream (H2D):  Qin[b_i, b_i+1)                         -> AoS staging
+//     compute stream:     transpose chunk i -> Q[0]; CFL sweep of chunk i -> cache rows, TRUE max(lambda) accumulates in its own slot;
+//                         fused step of the window [b_i - 2, b_i+1) with ghost cells at both ends, dt from the HINT
+//                         -> cells [b_i - 1, b_i+1 - 1) of Q[1] are final; transpose them -> AoS output staging
+//     copy stream (D2H):  -> Qout
+//   so that H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 run at the same time (full-duplex link).
+// At the end the true max(lambda) of the uploaded data is compared with the hint, bit for bit.  Equal (every call of a solver loop
+// but the first): done -- dt depends on nothing else, so the result is bit-identical to upload + step + download.  Different
+// (first call, state edited by the caller): the step is redone from the intact structure-of-arrays input on the device with the
+// right dt, and downloaded chunk by chunk (transpose of chunk i+1 overlapping D2H of chunk i).
+// ---------------------------------------------------------------------------------------------
+static int64_t host_chunk_cells() {   // (read at every call: tests shrink it)
+  const char* e = std::getenv("HS_HOST_CHUNK");
+  long long x = e ? std::atoll(e) : (1ll << 19);
+  if (x < 1024) x = 1024;
+  return (int64_t)(x & ~1ll);
+}
+
+static int ensure_pipeline(hs_ctx* c, Part& p, int nchunks) {
+  if (!p.s_h2d) CU(cudaStreamCreateWithFlags(&p.s_h2d, cudaStreamNonBlocking));
+  if (!p.s_d2h) CU(cudaStreamCreateWithFlags(&p.s_d2h, cudaStreamNonBlocking));
+  if (!p.stage_out) CU(cudaMalloc(&p.stage_out, (size_t)c->nvar * p.prob.stride * sizeof(double)));
+  if (!p.scal_sweep) CU(cudaMalloc(&p.scal_sweep, sizeof(double) * HS_SCAL_DOUBLES(1)));
+  while ((int)p.ev_in.size() < nchunks) {
+    cudaEvent_t a, b;
+    CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    p.ev_in.push_back(a); p.ev_out.push_back(b);
+  }
+  return ensure_stage(c, p);
+}
+
+static hsd_problem_t window_of(const hsd_problem_t& whole, int64_t ncells) {
+  hsd_problem_t w = whole;   // same model / EoS / row pitch (stride), fewer cells
+  w.ncells = ncells; w.nprob = 1;
+  return w;
+}
+
+static int step_host_pipelined(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin, double* Qout, double* dt_out) {
+  Part& p = c->parts[0];
+  PART_ENTER(p);
+  const int64_t N = c->ncells, nvar = c->nvar, CH = host_chunk_cells();
+  // Chunk boundaries (all even).  The first and the last chunks are short (CH/8, CH/4, CH/2, then CH): the D2H stream starts
+  // working after the first chunk's H2D + kernels and the tail after the last H2D is one short chunk, so the fill / drain of the
+  // pipeline costs ~1/8 of a chunk time at each end instead of a whole one.
+  std::vector<int64_t> bnd;
+  {
+    std::vector<int64_t> head, tail;
+    int64_t lo = 0, hi = N;
+    for (int64_t sz = CH / 8; sz < CH && hi - lo > 4 * CH; sz *= 2) {
+      const int64_t e = sz & ~1ll;
+      head.push_back(lo); lo += e;
+      hi -= e; tail.push_back(hi);
+    }
+    bnd = head;
+    for (int64_t x = lo; x < hi; x += CH) bnd.push_back(x);
+    for (auto it = tail.rbegin(); it != tail.rend(); ++it) bnd.push_back(*it);
+    bnd.push_back(N);
+  }
+  const int K = (int)bnd.size() - 1;
+  int rc = ensure_pipeline(c, p, K); if (rc) return rc;
+  rc = ensure_hist(c, 1); if (rc) return rc;
+  auto b_of = [&](int i) -> int64_t { return bnd[i > K ? K : i]; };
+
+  // the hint: max(lambda) of the state the context holds now (what the previous call returned)
+  unsigned long long hint_bits = 0;
+  if (c->has_state) {
+    CU(cudaMemcpyAsync(&hint_bits, hsd_scal_lambda_cur(p.scal, 1, c->n), sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+    CU(cudaStreamSynchronize(p.stream));
+  }
+  double hint;
+  std::memcpy(&hint, &hint_bits, sizeof hint);
+  const bool spec = c->has_state && hint > 0.0 && hint < 1.0e300;
+  c->has_state = false;   // (set again on success)
+
+  // scalar blocks: the context's own block drives the step (slot 0 = hint), the sweep accumulates the true max(lambda) in its own
+  CU(cudaMemsetAsync(p.scal, 0, sizeof(double) * HS_SCAL_DOUBLES(1), p.stream));
+  CU(cudaMemsetAsync(p.scal_sweep, 0, sizeof(double) * HS_SCAL_DOUBLES(1), p.stream));
+  if (spec) CU(cudaMemcpyAsync(p.scal, &hint_bits, sizeof(double), cudaMemcpyHostToDevice, p.stream));
+  cudaEvent_t ev0 = p.ev_out[0];   // (reused below only after the copy streams have waited on it)
+  CU(cudaEventRecord(ev0, p.stream));
+  CU(cudaStreamWaitEvent(p.s_h2d, ev0, 0));   // staging buffers of the previous call are free (its D2H was synchronised before it returned)
+
+  const size_t cellb = (size_t)nvar * sizeof(double);
+  for (int i = 0; i < K; ++i) {
+    const int64_t b0 = b_of(i), b1 = b_of(i + 1);
+    CU(cudaMemcpyAsync(p.stage + b0 * nvar, Qin + b0 * nvar, (size_t)(b1 - b0) * cellb, cudaMemcpyHostToDevice, p.s_h2d));
+    CU(cudaEventRecord(p.ev_in[i], p.s_h2d));
+    CU(cudaStreamWaitEvent(p.stream, p.ev_in[i], 0));
+    rc = transpose_range(c->model, true, p.stage + b0 * nvar, p.Q[0] + b0, b1 - b0, p.prob.stride, p.stream); if (rc) return rc;
+    const hsd_problem_t wsw = window_of(p.prob, b1 - b0);
+    rc = wave_bounds_impl(&wsw, p.Q[0] + b0, p.aux[0] + b0, p.scal_sweep, 0, nullptr, p.stream, true); if (rc) return rc;
+    if (spec) {
+      const int64_t w0 = i ? b0 - 2 : 0;                       // window [w0, b1): ghost cell at each end that is not a physical boundary
+      const int ghost = (i ? 1 : 0) | (i < K - 1 ? 2 : 0);
+      const hsd_problem_t wst = window_of(p.prob, b1 - w0);
+      rc = hsd_step(&wst, flux, cfl, dx, 1.0e300, 0, p.Q[0] + w0, p.aux[0] + w0, p.Q[1] + w0, p.aux[1] + w0, p.scal,
+                    i == 0 ? p.dt_hist : nullptr, 0, 1, ghost, p.stream);
+      if (rc) return rc;
+      const int64_t u0 = i ? b0 - 1 : 0, u1 = (i < K - 1) ? b1 - 1 : N;   // cells this window made final
+      rc = transpose_range(c->model, false, p.Q[1] + u0, p.stage_out + u0 * nvar, u1 - u0, p.prob.stride, p.stream); if (rc) return rc;
+      CU(cudaEventRecord(p.ev_out[i], p.stream));
+      CU(cudaStreamWaitEvent(p.s_d2h, p.ev_out[i], 0));
+      CU(cudaMemcpyAsync(Qout + u0 * nvar, p.stage_out + u0 * nvar, (size_t)(u1 - u0) * cellb, cudaMemcpyDeviceToHost, p.s_d2h));
+    }
+  }
+  unsigned long long true_bits = 0;
+  CU(cudaMemcpyAsync(&true_bits, p.scal_sweep, sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+  int st_sweep = 0;
+  CU(cudaMemcpyAsync(&st_sweep, scal_status(p.scal_sweep, 1), sizeof(int), cudaMemcpyDeviceToHost, p.stream));
+  CU(cudaStreamSynchronize(p.stream));
+  c->pipelined_calls += 1;
+  if (spec && true_bits == hint_bits) {
+    // every window counted one step: the grid took one
+    const long long one = 1;
+    CU(cudaMemcpyAsync(scal_steps(p.scal, 1), &one, sizeof one, cudaMemcpyHostToDevice, p.stream));
+    if (dt_out) CU(cudaMemcpyAsync(dt_out, p.dt_hist, sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+    CU(cudaStreamSynchronize(p.stream));
+    CU(cudaStreamSynchronize(p.s_d2h));
+    c->n = 1;
+    c->has_state = true;
+    c->speculation_hits += 1;
+    const int rs = read_status(c);
+    if (rs) return rs;
+    return st_sweep ? fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError") : HS_OK;
+  }
+  // no usable hint: the step is (re)done from the intact input with dt from the true max(lambda)
+  if (spec) CU(cudaStreamSynchronize(p.s_d2h));
+  CU(cudaMemsetAsync(p.scal, 0, sizeof(double) * HS_SCAL_DOUBLES(1), p.stream));
+  CU(cudaMemcpyAsync(p.scal, p.scal_sweep, sizeof(double), cudaMemcpyDeviceToDevice, p.stream));
+  c->n = 0;
+  rc = enqueue_step(c, flux, cfl, dx, 1.0e300, 0, 1); if (rc) return rc;
+  if (dt_out) CU(cudaMemcpyAsync(dt_out, p.dt_hist, sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+  for (int i = 0; i < K; ++i) {
+    const int64_t b0 = b_of(i), b1 = b_of(i + 1);
+    rc = transpose_range(c->model, false, p.Q[1] + b0, p.stage_out + b0 * nvar, b1 - b0, p.prob.stride, p.stream); if (rc) return rc;
+    CU(cudaEventRecord(p.ev_out[i], p.stream));
+    CU(cudaStreamWaitEvent(p.s_d2h, p.ev_out[i], 0));
+    CU(cudaMemcpyAsync(Qout + b0 * nvar, p.stage_out + b0 * nvar, (size_t)(b1 - b0) * cellb, cudaMemcpyDeviceToHost, p.s_d2h));
+  }
+  CU(cudaStreamSynchronize(p.stream));
+  CU(cudaStreamSynchronize(p.s_d2h));
+  c->has_state = true;
+  const int rs = read_status(c);
+  if (rs) return rs;
+  return st_sweep ? fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError") : HS_OK;
+}
+
+int hs_step_host(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin, double* Qout, double* dt_out) {
+  if (!c) return fail(HS_ERR_ARG, "null context");
+  if (!Qin || !Qout) return fail(HS_ERR_ARG, "null Q");
+  if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
+  const char* eoff = std::getenv("HS_HOST_PIPELINE");
+  const bool off = eoff && eoff[0] == '0';
+  // one grid on one device with at least two chunks: the pipelined form; everything else (ensembles, several devices,
+  // small grids, odd cell counts) takes upload + step + download
+  const bool pipe = !off && c->parts.size() == 1 && c->nprob == 1 && c->ncells % 2 == 0 && c->ncells >= 2 * host_chunk_cells();
+  if (!pipe) {
+    const int rc = step_host_plain(c, flux, cfl, dx, Qin, Qout, dt_out);
+    return rc;
+  }
+  return step_host_pipelined(c, flux, cfl, dx, Qin, Qout, dt_out);
+}
+
+int hs_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(HS_ERR_ARG, "null buffer");
+  if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return HS_OK; }
+  CU(e);
+  return HS_OK;
+}
+
+int hs_host_unregister(void* ptr) {
+  if (!ptr) return fail(HS_ERR_ARG, "null buffer");
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return HS_OK; }
+  CU(e);
+  return HS_OK;
+}
+
+int hs_step_host_stats(hs_ctx_t* c, int64_t* pipelined_calls, int64_t* speculation_hits) {
+  if (!c) return fail(HS_ERR_ARG, "null context");
+  if (pipelined_calls) *pipelined_calls = c->pipelined_calls;
+  if (speculation_hits) *speculation_hits = c->speculation_hits;
+  return HS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

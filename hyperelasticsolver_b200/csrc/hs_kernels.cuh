@@ -940,12 +940,22 @@ __global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, doub
 #pragma unroll
     for (int v = 0; v < 13; ++v) rec[sp_slot(v)] = __ldg(Q + (size_t)v * stride + gi);
   }
+  // The same instruction sequence as the CFL sweep at the tail of the fused step kernels (phase_state<.., WITH_H> + the Newton
+  // largest-eigenvalue solve), so that the cache rows of an uploaded state are BIT-IDENTICAL to the rows the step that produced
+  // that state left behind: a host-resident loop (upload + step + download per step) then reproduces the device-resident loop bit
+  // for bit.  Only the full get_eigvals output (all three speeds) takes the Jacobi solve.
   PhaseState st;
-  phase_state<GEN>(eos, (MODEL == MODEL_MPH30) ? rec[0] : 1.0, rec + 2, rec[5], rec + 6, st);
-  double S6[6], ev[3];
-  phase_acoustic_sym(eos, st, S6);
-  if (eig_full) sym3_eigs_jacobi(S6, ev); else sym3_eigs(S6, ev);
-  const double cm = sqrt(fmax(fabs(ev[2]), fabs(ev[0])));
+  phase_state<GEN, MODEL == MODEL_SP13, true>(eos, (MODEL == MODEL_MPH30) ? rec[0] : 1.0, rec + 2, rec[5], rec + 6, st);
+  double ev[3] = {0.0, 0.0, 0.0};
+  double cm;
+  if (eig_full) {
+    double S6[6];
+    phase_acoustic_sym<true>(eos, st, S6);
+    sym3_eigs_jacobi(S6, ev);
+    cm = sqrt(fmax(fabs(ev[2]), fabs(ev[0])));
+  } else {
+    cm = phase_cmax<true>(eos, st);
+  }
   double lo_c = st.u[0] - cm, hi_c = st.u[0] + cm;
   if (NPH == 2) {
     lo_c = fmin(lo_c, __shfl_xor_sync(FULL, lo_c, 1));
@@ -962,7 +972,7 @@ __global__ void __launch_bounds__(T) k_bounds(const double* __restrict__ Q, doub
 #pragma unroll
       for (int r = 0; r < 3; ++r) aux[(size_t)(SP_R_SG + r) * stride + gi] = st.sig1[r];
     }
-    lamv = fmax(fabs(lo_c), fabs(hi_c));
+    lamv = fmax(fabs(lo_c), fabs(hi_c));   // (single-phase: == |u1| + c_max bit for bit, as the step kernel forms it)
     if (eig_full) {  // [u1 + c_k (ascending), u1 - c_k], HyperelasticityMPh.jl:263-265
       double* e = eig_full + (size_t)gi * (6 * NPH) + 6 * ph;
 #pragma unroll

@@ -10,7 +10,7 @@ import numpy as np
 from . import _lib as L
 from .testcases import riemann_grid
 
-__all__ = ["Solver", "initial_condition", "update_cell"]
+__all__ = ["Solver", "initial_condition", "update_cell", "register_host", "unregister_host"]
 
 _FLUX = {"hll": L.HLL, "lxf": L.LXF, L.HLL: L.HLL, L.LXF: L.LXF}
 
@@ -32,6 +32,8 @@ class Solver:
         self.model, self.nvar = model, L.NVAR[model]
         self.ncells, self.nprob, self.device = int(ncells), int(nprob), int(device)
         self._ctx = C.c_void_p()
+        self.t = np.zeros(self.nprob)
+        self.steps = np.zeros(self.nprob, dtype=np.int64)
         self._eos = L.eos_array(eos, model)
         if devices is not None and len(devices) > 1:
             devs = (C.c_int * len(devices))(*[int(d) for d in devices])
@@ -117,7 +119,26 @@ class Solver:
         Qout = np.empty_like(Qin) if Qout is None else Qout
         dt = np.empty(self.nprob)
         L.check(L.lib().hs_step_host(self._ctx, _FLUX[flux], float(cfl), float(dx), Qin.ctypes.data, Qout.ctypes.data, dt.ctypes.data))
+        self.t = dt.copy()                                   # the context is left as upload + one step leave it
+        self.steps = np.ones(self.nprob, dtype=np.int64)
         return Qout, dt
+
+    def step_host_stats(self):
+        """(calls of step_host that took the chunk-pipelined form, how many of them had their hinted max(lambda) confirmed)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        L.check(L.lib().hs_step_host_stats(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+
+def register_host(arr):
+    """Page-lock a numpy array (hs_host_register) so that upload / download / step_host copy at the link rate and the chunks of
+    step_host overlap; returns the array.  Release with unregister_host."""
+    L.check(L.lib().hs_host_register(arr.ctypes.data, arr.nbytes))
+    return arr
+
+
+def unregister_host(arr):
+    L.check(L.lib().hs_host_unregister(arr.ctypes.data))
 
 
 def update_cell(Q3, flux_num, eigvals_or_lambda, dtdx_or_eos, eos=None, device=0):

@@ -24,6 +24,7 @@
 #ifndef HYPERELASTIC_B200_H
 #define HYPERELASTIC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -92,11 +93,24 @@ int hs_advance(hs_ctx_t* ctx, int flux, double cfl, double dx, double t_end, int
                double* t_io, int64_t* step_io, double* dt_hist);
 
 /* One step on HOST arrays: upload Qin, step, download into Qout (may alias Qin).  This is the
- * literal drop-in for one iteration of main.jl:202-227 with Q0 living in Julia memory;
- * the whole state crosses the host link once in each direction per call (the copies cannot overlap: dt needs
- * max(lambda) of the complete uploaded state), so this form is bound by the link, not by the kernels. */
+ * literal drop-in for one iteration of main.jl:202-227 with Q0 living in Julia memory; the whole state crosses
+ * the host link once in each direction per call.  One grid on one device is processed chunk by chunk with the
+ * H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlapping (full-duplex link):
+ * dt = cfl dx / max(lambda) needs the CFL sweep of the whole uploaded state, so the step runs speculatively with the
+ * max(lambda) the previous call's fused step produced for the state it returned, the sweep of the uploaded data
+ * confirms it bit for bit at the end, and on a mismatch (first call, state edited in between) the step is redone on
+ * the device with the right dt -- the result is always bit-identical to hs_upload + hs_step + hs_download.
+ * The copies only overlap from page-locked memory: register the arrays once with hs_host_register (a Julia Array,
+ * a numpy array ... are pageable).  HS_HOST_PIPELINE=0 forces upload + step + download; HS_HOST_CHUNK = cells per chunk. */
 int hs_step_host(hs_ctx_t* ctx, int flux, double cfl, double dx, const double* Qin, double* Qout,
                  double* dt_out);
+/* page-lock / release a host array (cudaHostRegister, portable) so that hs_upload / hs_download / hs_step_host copy
+ * at the link rate and asynchronously; registering twice / releasing an unregistered array is not an error */
+int hs_host_register(void* ptr, size_t bytes);
+int hs_host_unregister(void* ptr);
+/* bookkeeping of hs_step_host on this context: calls that took the pipelined form, and how many of them found the
+ * hinted max(lambda) confirmed (no redo) */
+int hs_step_host_stats(hs_ctx_t* ctx, int64_t* pipelined_calls, int64_t* speculation_hits);
 
 /* ------------------------------------------------------------------------------------------
  * Stateless batches: literal drop-ins for the per-cell / per-face Julia functions.

@@ -17,7 +17,9 @@
 module HyperelasticB200
 
 export Barton2009, Hank2016, energy, pressure, stress, prim2cons_mph, cons2prim_mph, flux_mph, noncons_flux, get_eigvals, lxf, hll,
-       Solver, upload!, download!, step!, advance!, wave_speeds, destroy!
+       initial_states, initial_condition, initial_condition_tanh, update_cell,
+       Solver, upload!, download!, step!, step_host!, advance!, set_time!, wave_speeds, destroy!, host_register!, host_unregister!,
+       SinglePhase
 
 const LIB = get(ENV, "HYPERELASTIC_B200_LIB", joinpath(@__DIR__, "..", "hyperelasticsolver_b200", "libhyperelastic_b200.so"))
 
@@ -99,10 +101,129 @@ function lxf(eos::Tuple{Barton2009,Barton2009}, Q_l::VecOrMat{Float64}, Q_r::Vec
   return cons, dm, dp
 end
 
+# --- host-side setup of main.jl that does not touch physics -------------------------------------------
+# initial_states(eos, testcase) -> (Ql, Qr): the tables of HyperelasticityMPh.jl:275-426, primitives assembled as at
+# :412-420 (nominal density den/det(F), F splatted column-major) and converted with prim2cons_mph (:422-423).
+const _I3 = [1.0 0 0; 0 1 0; 0 0 1]
+const _F3 = [1.0 0 0; -0.01 0.95 0.02; -0.015 0 0.9]
+const _F4L = [0.98 0 0; 0.02 1 0.1; 0 0 1]
+const _F4R = [1.0 0 0; 0 1 0.1; 0 0 1]
+const _F5R = [1.0 0 0; 0.015 0.95 0; -0.01 0 0.9]
+# testcase => (alpha_l_1, alpha_l_2, alpha_r_1, alpha_r_2, den, u_l, S_l, F_l, u_r, S_r, F_r); the alpha values are the
+# reference's own literals (0.1 is a literal, not 1 - 0.9: HyperelasticityMPh.jl:349-352)
+const _MPH_CASES = Dict(
+  1 => (0.5, 0.5, 0.5, 0.5, 5.0, [0.0, 0, 0], 0.0, _I3, [0.0, 0, 0], 0.0, _I3),
+  2 => (0.5, 0.5, 0.5, 0.5, 5.0, [1.0, 0, 0], 0.0, _I3, [1.0, 0, 0], 0.0, _I3),
+  3 => (0.5, 0.5, 0.5, 0.5, 8.9, [2.0, 0.0, 0.1], 0.0, _F3, [2.0, 0.0, 0.1], 0.0, _F3),
+  4 => (0.5, 0.5, 0.5, 0.5, 8.9, [0.0, 0.5, 1.0], 1e-3, _F4L, [0.0, 0.0, 0.0], 0.0, _F4R),
+  5 => (0.5, 0.5, 0.5, 0.5, 8.9, [2.0, 0.0, 0.1], 0.0, _F3, [0.0, -0.03, -0.01], 0.0, _F5R),
+  6 => (0.1, 0.9, 0.9, 0.1, 8.9, [0.0, 0.5, 1.0], 1.0e-3, _F4L, [0.0, 0.0, 0.0], 0.0, _F4R),
+  7 => (0.1, 0.9, 0.9, 0.1, 8.9, [2.0, 0.0, 0.1], 0.0, _F3, [0.0, -0.03, -0.01], 0.0, _F5R),
+  10 => (0.4, 0.6, 0.6, 0.4, 8.9, [2.0, 0.0, 0.1], 0.0, _F3, [2.0, 0.0, 0.1], 0.0, _F3))
+_det3(F) = F[1,1]*(F[2,2]*F[3,3]-F[2,3]*F[3,2]) - F[1,2]*(F[2,1]*F[3,3]-F[2,3]*F[3,1]) + F[1,3]*(F[2,1]*F[3,2]-F[2,2]*F[3,1])
+function initial_states(eos::Tuple{Barton2009,Barton2009}, testcase::Integer; device::Integer=0)
+  haskey(_MPH_CASES, testcase) || error("unknown multiphase test case $testcase")
+  (al1, al2, ar1, ar2, den, ul, Sl, Fl, ur, Sr, Fr) = _MPH_CASES[testcase]
+  dl = den / _det3(Fl); dr = den / _det3(Fr)
+  Pl = Float64[al1, dl, ul..., Sl, Fl..., al2, dl, ul..., Sl, Fl...]     # F... splats column-major (:417-420)
+  Pr = Float64[ar1, dr, ur..., Sr, Fr..., ar2, dr, ur..., Sr, Fr...]
+  return prim2cons_mph(eos, Pl; device=device), prim2cons_mph(eos, Pr; device=device)
+end
+
+# main.jl:99-106
+function initial_condition(Ql::Vector{Float64}, Qr::Vector{Float64}, nx::Integer)
+  Q0 = Array{Float64}(undef, length(Ql), nx)
+  for i in 1:nx
+    Q0[:, i] = (i - 1) < nx / 2 ? Ql : Qr
+  end
+  return Q0
+end
+
+# main.jl:110-123: volume fraction smoothed with tanh across `width` around x0; the other primitives of the left state
+function initial_condition_tanh(eos::Tuple{Barton2009,Barton2009}, Ql::Vector{Float64}, Qr::Vector{Float64}, nx::Integer; x0=0.5, width=0.05, device::Integer=0)
+  Pl = cons2prim_mph(eos, Ql; device=device); Pr = cons2prim_mph(eos, Qr; device=device)
+  P = Array{Float64}(undef, 30, nx)
+  for i in 1:nx
+    x = (i - 0.5) / nx
+    w = 0.5 * (1 + tanh((x - x0) / width))
+    P[:, i] = Pl
+    P[1, i] = (1 - w) * Pl[1] + w * Pr[1]
+    P[16, i] = 1 - P[1, i]
+  end
+  return prim2cons_mph(eos, P; device=device)
+end
+
+# update_cell, main.jl:30-41 (LxF) and :43-60 (HLL), on one 3-cell stencil Q (nvar x 3), as the reference defines them
+function update_cell(Q::Array{Float64,2}, flux_num::Function, lambda, eos::Tuple{Barton2009,Barton2009})
+  Q_l, Qc, Q_r = Q[:, 1], Q[:, 2], Q[:, 3]
+  F_l, _, NF_l = flux_num(eos, Q_l, Qc, lambda)
+  F_r, NF_r, _ = flux_num(eos, Qc, Q_r, lambda)
+  return Qc - 1.0 / lambda * ((F_r - F_l) + (NF_r + NF_l))
+end
+function update_cell(Q::Array{Float64,2}, flux_num::Function, eigvals, dtdx, eos::Tuple{Barton2009,Barton2009})
+  Q_l, Qc, Q_r = Q[:, 1], Q[:, 2], Q[:, 3]
+  F_l, _, NF_l = flux_num(eos, Q_l, Qc, eigvals[1:2])
+  F_r, NF_r, _ = flux_num(eos, Qc, Q_r, eigvals[2:3])
+  return Qc - dtdx * ((F_r - F_l) + (NF_r + NF_l))
+end
+
+# page-lock a Julia Array so that upload! / download! / step_host! copy at the link rate and the chunks of step_host!
+# overlap (a Julia Array is pageable memory); call once per array, release before the array is freed
+host_register!(A::Array{Float64}) = (GC.@preserve A check(ccall((:hs_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), A, sizeof(A))); A)
+host_unregister!(A::Array{Float64}) = (GC.@preserve A check(ccall((:hs_host_unregister, LIB), Cint, (Ptr{Cvoid},), A)); A)
+
+# --- single-phase 13-variable model (Hyperelasticity.jl; SURVEY.md A.6) ----------------------------------
+# Q = [rho*u(3), rho*F(9, row-major), rho*E], primitives P = [u(3), F(9 row-major), S] = the arguments of
+# prim2cons (Hyperelasticity.jl:70).  Same names as the reference module, inside a sub-module because the
+# two-phase methods above already own `get_eigvals` / `initial_states` for Tuple{Barton2009,Barton2009}.
+module SinglePhase
+  import ..Barton2009, ..check, ..LIB, ..HS_MODEL_SP13, ..ncols
+  export prim2cons, cons2prim, flux, get_eigvals, initial_states
+  for (jl, c) in ((:prim2cons, :hs_prim2cons), (:cons2prim, :hs_cons2prim), (:flux, :hs_flux))
+    @eval function $jl(eos::Barton2009, X::VecOrMat{Float64}; device::Integer=0)
+      Y = similar(X); e = [eos]
+      GC.@preserve X Y e check(ccall(($(QuoteNode(c)), LIB), Cint,
+          (Cint, Ptr{Barton2009}, Cint, Ptr{Float64}, Ptr{Float64}, Int64, Cint),
+          HS_MODEL_SP13, e, 1, X, Y, ncols(X), device))
+      return Y
+    end
+  end
+  function get_eigvals(eos::Barton2009, Q::VecOrMat{Float64}, n::Array{<:Any,1}=[1, 0, 0]; device::Integer=0)
+    nn = Vector{Float64}(n); e = [eos]
+    E = Q isa AbstractVector ? zeros(6) : zeros(6, size(Q, 2))
+    GC.@preserve Q E e nn check(ccall((:hs_get_eigvals, LIB), Cint,
+        (Cint, Ptr{Barton2009}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Cint), HS_MODEL_SP13, e, 1, Q, nn, E, ncols(Q), device))
+    return E
+  end
+  const _R3 = sqrt(3.0)
+  const _ROT = [0.5 -0.5*_R3 0; 0.5*_R3 0.5 0; 0 0 1.0]
+  # Hyperelasticity.jl:124-172 (F is written row-major into P, :81-86)
+  function initial_states(eos::Barton2009, testcase::Integer; device::Integer=0)
+    rowmajor(F) = vec(permutedims(F))
+    (ul, Fl, Sl, ur, Fr, Sr) =
+      testcase == 1 ? ([0.0, 0.5, 1.0], [0.98 0 0; 0.02 1 0.1; 0 0 1], 1e-3, [0.0, 0.0, 0.0], [1.0 0 0; 0 1 0.1; 0 0 1], 0.0) :
+      testcase == 2 ? ([2.0, 0.0, 0.1], [1.0 0 0; -0.01 0.95 0.02; -0.015 0 0.9], 0.0, [0.0, -0.03, -0.01], [1.0 0 0; 0.015 0.95 0; -0.01 0 0.9], 0.0) :
+      testcase == 3 ? ([1.0, 0.0, 0.0], _ROT, 0.0, [1.0, 0.0, 0.0], _ROT, 0.0) :
+                      ([0.0, 0.0, 0.0], [1.0 0 0; 0 1 0; 0 0 1], 0.0, [0.0, 0.0, 0.0], [1.0 0 0; 0 1 0; 0 0 1], 0.0)
+    Pl = Float64[ul..., rowmajor(Fl)..., Sl]; Pr = Float64[ur..., rowmajor(Fr)..., Sr]
+    return prim2cons(eos, Pl; device=device), prim2cons(eos, Pr; device=device)
+  end
+end # module SinglePhase
+
 # --- device-resident time loop (main.jl:202-227) ---------------------------------------------------
 mutable struct Solver
   ctx::Ptr{Cvoid}
   nvar::Int; ncells::Int; nprob::Int
+end
+
+# single-phase solver: Solver(eos::Barton2009, ncells; ...)
+function Solver(eos::Barton2009, ncells::Integer; nprob::Integer=1, device::Integer=0)
+  ref = Ref{Ptr{Cvoid}}(C_NULL); e = [eos]
+  GC.@preserve e check(ccall((:hs_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Barton2009}, Cint, Int64, Int64, Cint),
+      ref, HS_MODEL_SP13, e, 1, ncells, nprob, device))
+  s = Solver(ref[], 13, ncells, nprob)
+  finalizer(destroy!, s)
+  return s
 end
 
 # devices = [0, 1, ..., 7]: several GPUs of this process (hs_create_multi): one grid is slab-decomposed,
@@ -140,6 +261,19 @@ function step!(s::Solver, flux::Function, cfl, dx)
       s.ctx, flux === hll ? HS_FLUX_HLL : HS_FLUX_LXF, cfl, dx, dt))
   return s.nprob == 1 ? dt[1] : dt
 end
+
+# one pass of main.jl:204-227 on HOST arrays (Q1 may be Q0): the literal drop-in with the state in Julia memory.  The library
+# overlaps the H2D copy, the kernels and the D2H copy chunk by chunk (hs_step_host); host_register!(Q0), host_register!(Q1) once
+# beforehand makes the copies asynchronous and link-rate.  Returns dt.
+function step_host!(s::Solver, flux::Function, cfl, dx, Q0::Array{Float64}, Q1::Array{Float64})
+  dt = zeros(s.nprob)
+  GC.@preserve Q0 Q1 dt check(ccall((:hs_step_host, LIB), Cint, (Ptr{Cvoid}, Cint, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+      s.ctx, flux === hll ? HS_FLUX_HLL : HS_FLUX_LXF, cfl, dx, Q0, Q1, dt))
+  return s.nprob == 1 ? dt[1] : dt
+end
+
+# restart (main.jl:185-186): set the clock of every problem
+set_time!(s::Solver, t, step_num) = check(ccall((:hs_set_time, LIB), Cint, (Ptr{Cvoid}, Float64, Int64), s.ctx, t, step_num))
 
 # `while t < T` without returning to the host between steps; returns (t, step_num)
 function advance!(s::Solver, flux::Function, cfl, dx, T; t=0.0, step_num=0, max_steps=typemax(Int32))
