@@ -2,6 +2,7 @@
 // reference interfaces each entry point replaces).  Host side only: argument checks, device
 // memory, launches.  There is no CPU compute path in this file by design.
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -778,21 +779,17 @@ static int step_host_pipelined(hs_ctx_t* c, int flux, double cfl, double dx, con
   Part& p = c->parts[0];
   PART_ENTER(p);
   const int64_t N = c->ncells, nvar = c->nvar, CH = host_chunk_cells();
-  // Chunk boundaries (all even).  The first and the last chunks are short (CH/8, CH/4, CH/2, then CH): the D2H stream starts
-  // working after the first chunk's H2D + kernels and the tail after the last H2D is one short chunk, so the fill / drain of the
-  // pipeline costs ~1/8 of a chunk time at each end instead of a whole one.
+  // Chunk boundaries (all even).  The first chunks are short (CH/32, CH/16, ... then CH), so the kernels and the D2H stream start
+  // working early; from then on equal chunks: D2H of chunk i runs beside H2D of chunk i+1, so the drain after the last H2D is one
+  // chunk's D2H (shrinking chunks at the end would only let the D2H stream fall behind).  Every copy costs ~25 us of link idle
+  // time, a chunk c/N of the ~36 ms the link needs: ~16-32 chunks is the optimum for a 2^24-cell single-phase grid (measured on
+  // B200 / PCIe Gen5: H2D alone 55.5 GB/s; both directions at once 48 GB/s each, i.e. 36.4 ms for 2 x 1.745 GB; this call 38.5 ms).
   std::vector<int64_t> bnd;
   {
-    std::vector<int64_t> head, tail;
-    int64_t lo = 0, hi = N;
-    for (int64_t sz = CH / 8; sz < CH && hi - lo > 4 * CH; sz *= 2) {
-      const int64_t e = sz & ~1ll;
-      head.push_back(lo); lo += e;
-      hi -= e; tail.push_back(hi);
-    }
-    bnd = head;
-    for (int64_t x = lo; x < hi; x += CH) bnd.push_back(x);
-    for (auto it = tail.rbegin(); it != tail.rend(); ++it) bnd.push_back(*it);
+    int64_t lo = 0;
+    for (int64_t sz = CH / 32; sz < CH && N - lo > 2 * CH + 4 * sz; sz *= 2) { bnd.push_back(lo); lo += sz & ~1ll; }
+    for (int64_t x = lo; x < N; x += CH) bnd.push_back(x);
+    if (bnd.size() > 1 && N - bnd.back() < CH / 4) bnd.pop_back();   // a short last chunk joins its neighbour
     bnd.push_back(N);
   }
   const int K = (int)bnd.size() - 1;
@@ -819,6 +816,14 @@ static int step_host_pipelined(hs_ctx_t* c, int flux, double cfl, double dx, con
   CU(cudaEventRecord(ev0, p.stream));
   CU(cudaStreamWaitEvent(p.s_h2d, ev0, 0));   // staging buffers of the previous call are free (its D2H was synchronised before it returned)
 
+  // HS_HOST_TRACE=1: per-call timeline of the three streams on stderr (development aid)
+  const bool trace = std::getenv("HS_HOST_TRACE") != nullptr;
+  cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};
+  const auto host_t0 = std::chrono::steady_clock::now();
+  if (trace) {
+    for (auto& e : tr) cudaEventCreate(&e);
+    cudaEventRecord(tr[0], p.stream);
+  }
   const size_t cellb = (size_t)nvar * sizeof(double);
   for (int i = 0; i < K; ++i) {
     const int64_t b0 = b_of(i), b1 = b_of(i + 1);
@@ -841,6 +846,16 @@ static int step_host_pipelined(hs_ctx_t* c, int flux, double cfl, double dx, con
       CU(cudaStreamWaitEvent(p.s_d2h, p.ev_out[i], 0));
       CU(cudaMemcpyAsync(Qout + u0 * nvar, p.stage_out + u0 * nvar, (size_t)(u1 - u0) * cellb, cudaMemcpyDeviceToHost, p.s_d2h));
     }
+  }
+  if (trace) {
+    cudaEventRecord(tr[1], p.s_h2d); cudaEventRecord(tr[2], p.stream); cudaEventRecord(tr[3], p.s_d2h);
+    const double enq = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    cudaEventSynchronize(tr[1]); cudaEventSynchronize(tr[2]); cudaEventSynchronize(tr[3]);
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, tr[0], tr[1]); cudaEventElapsedTime(&b, tr[0], tr[2]); cudaEventElapsedTime(&d, tr[0], tr[3]);
+    fprintf(stderr, "[hs_step_host] chunks %d spec %d: host enqueue %.2f ms; since start: H2D done %.2f, kernels done %.2f, D2H done %.2f ms\n",
+            K, (int)spec, enq, a, b, d);
+    for (auto& e : tr) cudaEventDestroy(e);
   }
   unsigned long long true_bits = 0;
   CU(cudaMemcpyAsync(&true_bits, p.scal_sweep, sizeof(double), cudaMemcpyDeviceToHost, p.stream));
@@ -892,7 +907,7 @@ int hs_step_host(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin
   const bool off = eoff && eoff[0] == '0';
   // one grid on one device with at least two chunks: the pipelined form; everything else (ensembles, several devices,
   // small grids, odd cell counts) takes upload + step + download
-  const bool pipe = !off && c->parts.size() == 1 && c->nprob == 1 && c->ncells % 2 == 0 && c->ncells >= 2 * host_chunk_cells();
+  const bool pipe = !off && c->parts.size() == 1 && c->nprob == 1 && c->ncells % 2 == 0 && c->ncells >= host_chunk_cells() / 2 && c->ncells >= 4096;
   if (!pipe) {
     const int rc = step_host_plain(c, flux, cfl, dx, Qin, Qout, dt_out);
     return rc;

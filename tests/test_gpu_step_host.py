@@ -99,7 +99,7 @@ def test_step_host_plain_paths(gpu, oracle):
             assert sol.step_host_stats() == (0, 0)
     finally:
         del os.environ["HS_HOST_PIPELINE"]
-    with hs.Solver(eos, 1 << 21, model=hm) as sol:       # default chunk (2^19 cells): 4 chunks, pageable numpy arrays
+    with hs.Solver(eos, 1 << 21, model=hm) as sol:       # default chunk size (2^21 cells: one chunk), pageable numpy arrays
         Q2, _ = sol.step_host(Q0)
         Q3, _ = sol.step_host(Q2)
         assert sol.step_host_stats() == (2, 1)
