@@ -59,10 +59,11 @@ EosPair eos_pair(const hsd_problem_t* p) {
   return e;
 }
 
-// per-problem scalar block layout inside `scal` (doubles): lam[3][nprob] | t[3][nprob] | steps[nprob] | status
+// per-problem scalar block layout inside `scal` (doubles): lam[3][nprob] | t[3][nprob] | steps[nprob] | hist_n[nprob] | status
 unsigned long long* scal_lam(double* s) { return reinterpret_cast<unsigned long long*>(s); }
 double* scal_t(double* s, int64_t nprob) { return s + 3 * nprob; }
 long long* scal_steps(double* s, int64_t nprob) { return reinterpret_cast<long long*>(s + 6 * nprob); }
+long long* scal_hist_n(double* s, int64_t nprob) { return reinterpret_cast<long long*>(s + 7 * nprob); }   // recorded-dt counters
 int* scal_status(double* s, int64_t nprob) { return reinterpret_cast<int*>(s + HS_SCAL_SLOTS * nprob); }
 
 // threads per block of the fused step / sweep kernels
@@ -189,6 +190,37 @@ int sp_tiles_per_block(int64_t ntiles) {
   return (int)k;
 }
 
+// quadrature-parallel two-phase step for small grids (k_step_qp): tiles of 16 cells, 12 warps per tile
+template <int FLUX, bool GEN, bool SAME>
+int launch_step_qp_s(StepArgs a, cudaStream_t st) {
+  constexpr size_t smem = qp_smem_doubles() * sizeof(double);
+  static std::atomic<unsigned> attr_dev_mask{0};
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (!(attr_dev_mask.load() & (1u << (dev & 31)))) {
+    CU(cudaFuncSetAttribute(k_step_qp<FLUX, GEN, SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev_mask.fetch_or(1u << (dev & 31));
+  }
+  a.tiles_per_prob = (a.ncells - 2 + (QP_CPB - 2) - 1) / (QP_CPB - 2);
+  const unsigned nb = (unsigned)a.tiles_per_prob * (unsigned)a.nprob;
+  k_step_qp<FLUX, GEN, SAME><<<nb, QP_T, smem, st>>>(a);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+int launch_step_qp(int flux, int gen, const StepArgs& a, cudaStream_t st) {
+  const bool same = std::memcmp(&a.eos.e[0], &a.eos.e[1], sizeof(EosDev)) == 0;
+#define HS_QP(F, G)  (same ? launch_step_qp_s<F, G, true>(a, st) : launch_step_qp_s<F, G, false>(a, st))
+  if (flux == HS_FLUX_HLL) return gen ? HS_QP(FLUX_HLL, true) : HS_QP(FLUX_HLL, false);
+  return gen ? HS_QP(FLUX_LXF, true) : HS_QP(FLUX_LXF, false);
+#undef HS_QP
+}
+// two-phase grids up to this many cells (all problems together) take k_step_qp; HS_QP_MAX_CELLS=0 disables it
+int64_t qp_max_cells() {
+  const char* e = std::getenv("HS_QP_MAX_CELLS");
+  return e ? std::atoll(e) : 2048;
+}
+
 template <int MODEL, int T>
 int launch_step_m(int flux, int gen, const StepArgs& a, int64_t nb, cudaStream_t st) {
   if (MODEL == MODEL_SP13) {
@@ -304,6 +336,7 @@ int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_e
   a.lam = scal_lam(scal); a.tt = scal_t(scal, p->nprob); a.steps = scal_steps(scal, p->nprob);
   a.status = scal_status(scal, p->nprob);
   a.dt_hist = dt_hist; a.hist_k = hist_k; a.hist_cap = dt_hist ? hist_cap : 0;
+  a.hist_n = scal_hist_n(scal, p->nprob);
   a.stride = p->stride; a.ncells = (int)p->ncells; a.nprob = (int)p->nprob;
   a.cur = (int)(n % 3); a.nxt = (int)((n + 1) % 3); a.clr = (int)((n + 2) % 3);
   a.ghost = ghost_mask;
@@ -312,6 +345,7 @@ int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_e
   a.spin_ns = spin_ns;
   a.eos = eos_pair(p);
   if (p->model == HS_MODEL_MPH30) {
+    if (p->ncells * p->nprob <= qp_max_cells()) return launch_step_qp(flux, p->gen, a, (cudaStream_t)stream);
     constexpr int T = T_STEP_MPH, CPB = T / 2;
     a.tiles_per_prob = (int)((p->ncells - 2 + (CPB - 2) - 1) / (CPB - 2));
     return launch_step_m<MODEL_MPH30, T>(flux, p->gen, a, (int64_t)a.tiles_per_prob * p->nprob, (cudaStream_t)stream);
@@ -397,6 +431,15 @@ struct hs_ctx {
   std::vector<void*> mailboxes;
   int64_t n = 0;              // launch counter since the last upload (selects buffers and scalar slots)
   uint64_t xseq = 0;          // exchange sequence number (never reused)
+  // hs_advance: six consecutive steps (the period of the buffer / scalar-slot rotation) captured as a CUDA graph and replayed;
+  // valid for one (flux, cfl, dx, t_end, history buffer) and for launches that start at n % 6 == n0
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    int flux = -1, n0 = -1;
+    double cfl = 0, dx = 0, t_end = 0;
+    const double* hist = nullptr;
+    int64_t hist_cap = 0;
+  } graph;
   bool has_state = false;     // the device holds a state with a valid max(lambda) slot (after upload / step / step_host)
   int64_t pipelined_calls = 0, speculation_hits = 0;   // hs_step_host bookkeeping (hs_step_host_stats)
   // host range (in cells / in problems) a part reads and writes
@@ -495,6 +538,7 @@ int hs_create_multi(hs_ctx_t** out, int model, const hs_barton2009_t* eos, int n
 
 int hs_destroy(hs_ctx_t* c) {
   if (!c) return HS_OK;
+  if (c->graph.exec) { cudaGraphExecDestroy(c->graph.exec); c->graph.exec = nullptr; }
   for (auto& p : c->parts) {
     DeviceGuard g(p.device);
     for (int k = 0; k < 2; ++k) { cudaFree(p.Q[k]); cudaFree(p.aux[k]); }
@@ -677,36 +721,85 @@ int hs_step(hs_ctx_t* c, int flux, double cfl, double dx, double* dt_out) {
   return read_status(c);
 }
 
+// Six steps from the current n as one graph launch (single-device contexts).  The graph is (re)captured when its key changes.
+static int launch_six_steps(hs_ctx* c, int flux, double cfl, double dx, double t_end, int64_t hist_cap) {
+  Part& p = c->parts[0];
+  PART_ENTER(p);
+  hs_ctx::StepGraph& G = c->graph;
+  const double* hist = hist_cap > 0 ? p.dt_hist : nullptr;
+  const int n0 = (int)(c->n % 6);
+  if (!G.exec || G.flux != flux || G.n0 != n0 || G.cfl != cfl || G.dx != dx || G.t_end != t_end || G.hist != hist || G.hist_cap != hist_cap) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    const int64_t n_save = c->n;
+    CU(cudaStreamBeginCapture(p.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = HS_OK;
+    for (int k = 0; k < 6 && rc == HS_OK; ++k) rc = enqueue_step(c, flux, cfl, dx, t_end, -1, hist_cap);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(p.stream, &graph);
+    c->n = n_save;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    CU(e);
+    const cudaError_t e2 = cudaGraphInstantiate(&G.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CU(e2);
+    G.flux = flux; G.n0 = n0; G.cfl = cfl; G.dx = dx; G.t_end = t_end; G.hist = hist; G.hist_cap = hist_cap;
+  }
+  CU(cudaGraphLaunch(G.exec, p.stream));
+  g_launches += 6;
+  c->n += 6;
+  return HS_OK;
+}
+
 int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64_t max_steps, double* t_io,
                int64_t* step_io, double* dt_hist) {
   if (!c) return fail(HS_ERR_ARG, "null context");
   if (max_steps < 0) return fail(HS_ERR_ARG, "max_steps < 0");
+  if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
   for (auto& p : c->parts) {
     PART_ENTER(p);
     const int64_t np = p.prob.nprob, off = c->first_prob(p);
     if (t_io) CU(cudaMemcpyAsync(hsd_scal_time(p.scal, np, c->n), t_io + off, sizeof(double) * np, cudaMemcpyHostToDevice, p.stream));
     if (step_io) CU(cudaMemcpyAsync(scal_steps(p.scal, np), step_io + off, sizeof(long long) * np, cudaMemcpyHostToDevice, p.stream));
+    CU(cudaMemsetAsync(scal_hist_n(p.scal, np), 0, sizeof(long long) * np, p.stream));   // the kernels index the dt history with these counters
   }
   const bool record = dt_hist && max_steps > 0;
   if (record) { int rc = ensure_hist(c, max_steps); if (rc) return rc; }
+  const int64_t hist_cap = record ? max_steps : 0;
+  // The loop stays on the device: steps are enqueued without waiting for them (on one device as replays of a six-step CUDA
+  // graph, so a grid too small to fill the GPU does not pay a launch per step), and the host only looks at the clock to decide
+  // how many more to enqueue.  One grid: the number is estimated from the current dt (it changes slowly), so a run of N steps
+  // needs a handful of synchronisations; kernels launched past t_end are no-ops (same overshoot semantics as main.jl:202,214).
+  const char* eg = std::getenv("HS_GRAPH");
+  const bool use_graph = c->parts.size() == 1 && !(eg && eg[0] == '0');
   std::vector<double> tv;
   int64_t done = 0;
-  const int64_t batch = 32;
   while (done < max_steps) {
-    // all problems finished?  (the kernels are no-ops past t_end, so over-launching is harmless)
     bool any = false;
+    double est = -1.0;
     for (auto& p : c->parts) {
       if (c->slabs && &p != &c->parts[0]) continue;
       PART_ENTER(p);
       const int64_t np = p.prob.nprob;
-      tv.resize(np);
+      tv.resize(np + 1);
       CU(cudaMemcpyAsync(tv.data(), hsd_scal_time(p.scal, np, c->n), sizeof(double) * np, cudaMemcpyDeviceToHost, p.stream));
+      if (c->nprob == 1) CU(cudaMemcpyAsync(tv.data() + 1, hsd_scal_lambda_cur(p.scal, 1, c->n), sizeof(double), cudaMemcpyDeviceToHost, p.stream));
       CU(cudaStreamSynchronize(p.stream));
       for (int64_t i = 0; i < np && !any; ++i) any = tv[i] < t_end;
+      if (c->nprob == 1 && any && tv[1] > 0.0) est = (t_end - tv[0]) / (cfl * dx / tv[1]);   // steps left at the current dt
     }
     if (!any) break;
-    const int64_t m = (max_steps - done < batch) ? (max_steps - done) : batch;
-    for (int64_t k = 0; k < m; ++k) { int rc = enqueue_step(c, flux, cfl, dx, t_end, done + k, record ? max_steps : 0); if (rc) return rc; }
+    int64_t m = 32;
+    if (est >= 0.0 && est < 1.0e15) {
+      m = (int64_t)est - 2;            // stop short of the estimate and look again (dt drifts by a few per cent over such a stretch)
+      if (m > 16384) m = 16384;
+      if (m < 1) m = 1;
+    }
+    if (m > max_steps - done) m = max_steps - done;
+    int64_t k = 0;
+    if (use_graph && m >= 12) {
+      for (; k + 6 <= m; k += 6) { int rc = launch_six_steps(c, flux, cfl, dx, t_end, hist_cap); if (rc) return rc; }
+    }
+    for (; k < m; ++k) { int rc = enqueue_step(c, flux, cfl, dx, t_end, -1, hist_cap); if (rc) return rc; }
     done += m;
   }
   for (auto& p : c->parts) {

@@ -146,10 +146,22 @@ __device__ __forceinline__ void noncons_column(const PhaseState& st, const doubl
   }
 }
 
-// acc += w * (column 1 of the non-conservative block): same arithmetic as noncons_column with
-// the quadrature weight folded into the common factors.  (Multiply by the reciprocal: a true FP64
-// division here costs ~10 % of the whole two-phase step.)
-__device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const double* A, double w, double* acc) {
+// HS_PHASE_CH = 1 (default since round 2: 1.642 vs 1.591 G cell-updates/s on the same box, GPU parity suite green): quadrature
+// states through phase_state_row1 (B = A A^T + Cayley-Hamilton, hs_phase.cuh) -- ~10 FP64 instructions fewer per state, results
+// differ by a few ulp.  0 = the full phase_state.
+#ifndef HS_PHASE_CH
+#define HS_PHASE_CH 1
+#endif
+// w * (column 1 of the non-conservative block) as 14 products factor x value (slot 1, the alpha*rho row, is identically zero):
+// same arithmetic as noncons_column with the quadrature weight folded into the common factors.  (Multiply by the reciprocal: a
+// true FP64 division here costs ~10 % of the whole two-phase step.)  The products are NOT formed here: the caller accumulates
+// acc = fma(factor, value, acc), node after node, so that the fused kernel (one thread walks over the nodes) and the
+// quadrature-parallel kernel for small grids (one warp per node, k_step_qp) round identically.
+//   factor index: 0 = w, 1 = w/(T1+T2), 2 = w/alpha, 3..5 = (w/alpha) A_1j;   value index k <-> slot (k == 0 ? 0 : k + 1)
+struct NcTerms { double f[6]; double X[14]; };
+__host__ __device__ constexpr int nc_factor(int k) { return k == 0 ? 0 : (k <= 4 ? 1 : ((k - 5) % 3 == 0 ? 2 : 3 + (k - 5) / 3)); }
+__host__ __device__ constexpr int nc_slot(int k) { return k == 0 ? 0 : k + 1; }
+__device__ __forceinline__ void noncons_terms(const PhaseState& st, const double* A, double w, NcTerms& t) {
   const double To = __shfl_xor_sync(FULL, st.T, 1);
   double uo[3], so[3];
 #pragma unroll
@@ -157,19 +169,45 @@ __device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const d
   const double uI[3] = {0.5 * st.u[0] + 0.5 * uo[0], 0.5 * st.u[1] + 0.5 * uo[1], 0.5 * st.u[2] + 0.5 * uo[2]};
   const double wi = w * hs_rcp(st.T + To);
   const double n0 = To * st.sig1[0] + st.T * so[0], n1 = To * st.sig1[1] + st.T * so[1], n2 = To * st.sig1[2] + st.T * so[2];
-  acc[0] += w * uI[0];
-  acc[2] += wi * n0; acc[3] += wi * n1; acc[4] += wi * n2;
-  acc[5] += wi * (n0 * uI[0] + n1 * uI[1] + n2 * uI[2]);
+  t.f[0] = w; t.f[1] = wi;
+  t.X[0] = uI[0];
+  t.X[1] = n0; t.X[2] = n1; t.X[3] = n2;
+  t.X[4] = n0 * uI[0] + n1 * uI[1] + n2 * uI[2];
   // rho F_1j u_1 + rho (F^T (u_I - u))_j: the two A_1j terms combine, A_1j (u_1 + (u_I - u)_1) = A_1j u_I1
   const double dv1 = uI[1] - st.u[1], dv2 = uI[2] - st.u[2];
   const double wia = w * st.inv_alpha;
+  t.f[2] = wia;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    const double t = wia * A[3 * j];
-    acc[6 + 3 * j] = fma(wia, fma(A[3 * j], uI[0], fma(A[3 * j + 1], dv1, A[3 * j + 2] * dv2)), acc[6 + 3 * j]);
-    acc[7 + 3 * j] = fma(t, st.u[1], acc[7 + 3 * j]);
-    acc[8 + 3 * j] = fma(t, st.u[2], acc[8 + 3 * j]);
+    t.f[3 + j] = wia * A[3 * j];
+    t.X[5 + 3 * j] = fma(A[3 * j], uI[0], fma(A[3 * j + 1], dv1, A[3 * j + 2] * dv2));
+    t.X[6 + 3 * j] = st.u[1];
+    t.X[7 + 3 * j] = st.u[2];
   }
+}
+__device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const double* A, double w, double* acc) {
+  NcTerms t;
+  noncons_terms(st, A, w, t);
+#pragma unroll
+  for (int k = 0; k < 14; ++k) acc[nc_slot(k)] = fma(t.f[nc_factor(k)], t.X[k], acc[nc_slot(k)]);
+}
+
+// The state of this thread's phase at the point base + s * delta of a straight path between two records (14 components: alpha,
+// momentum(3), energy, A(9) = slots 0, 2..14; slot 1 is never read).  One fused multiply-add per component.
+template <bool GEN>
+__device__ __forceinline__ void path_point(const EosDev& eos, const double* base14, const double* d14, double s, PhaseState& st, double* A) {
+  const double alpha = fma(s, d14[0], base14[0]);
+  double m[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m[k] = fma(s, d14[1 + k], base14[1 + k]);
+  const double E = fma(s, d14[4], base14[4]);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) A[k] = fma(s, d14[5 + k], base14[5 + k]);
+#if HS_PHASE_CH
+  phase_state_row1<GEN>(eos, alpha, m, E, A, st);
+#else
+  phase_state<GEN>(eos, alpha, m, E, A, st);
+#endif
 }
 
 // acc[j] += dalpha * sum_q w_q c_j(psi(s_q)) along the straight path between two records
@@ -178,12 +216,6 @@ __device__ __forceinline__ void noncons_accumulate(const PhaseState& st, const d
 //   FROM_END = false: psi(s) = base + s d          (base = start of the segment)
 //   FROM_END = true : psi(s) = base - (1 - s) d    (base = end of the segment)
 // i.e. one fused multiply-add per component instead of the two of Q_l (1-s) + Q_r s.  MPh only.
-// HS_PHASE_CH = 1 (default since round 2: 1.642 vs 1.591 G cell-updates/s on the same box, GPU parity suite green): quadrature
-// states through phase_state_row1 (B = A A^T + Cayley-Hamilton, hs_phase.cuh) -- ~10 FP64 instructions fewer per state, results
-// differ by a few ulp.  0 = the full phase_state.
-#ifndef HS_PHASE_CH
-#define HS_PHASE_CH 1
-#endif
 template <bool GEN, int T, bool FROM_END>
 __device__ __forceinline__ void path_integral(const EosDev& eos, const double* base, const double* d, const double* xs,
                                               const double* ws, double* acc, int& bad) {
@@ -192,22 +224,65 @@ __device__ __forceinline__ void path_integral(const EosDev& eos, const double* b
 #pragma unroll NODE_UNROLL
   for (int q = 0; q < 6; ++q) {
     const double s = FROM_END ? xs[q] - 1.0 : xs[q], w = ws[q] * dalpha;
-    const double alpha = fma(s, dalpha, base[0]);
-    double m[3], A[9];
+    double b14[14], d14[14], A[9];
+    b14[0] = base[0]; d14[0] = dalpha;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) m[k] = fma(s, d[(2 + k) * T], base[(2 + k) * T]);
-    const double E = fma(s, d[5 * T], base[5 * T]);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) A[k] = fma(s, d[(6 + k) * T], base[(6 + k) * T]);
+    for (int k = 1; k < 14; ++k) { b14[k] = base[(1 + k) * T]; d14[k] = d[(1 + k) * T]; }
     PhaseState st;
-#if HS_PHASE_CH
-    phase_state_row1<GEN>(eos, alpha, m, E, A, st);
-#else
-    phase_state<GEN>(eos, alpha, m, E, A, st);
-#endif
+    path_point<GEN>(eos, b14, d14, s, st, A);
     bad |= st.bad;
     noncons_accumulate(st, A, w, acc);
   }
+}
+
+// Component-wise pieces of hll_pathcons / lxf / update_cell with the rounding spelled out (explicit fused multiply-adds and
+// individually rounded products), shared by the fused kernel and the quadrature-parallel kernel for small grids so that both
+// produce the same bits.
+//   Q_hll = (Q_r s_r - Q_l s_l - (B_int + F_r - F_l)) / (s_r - s_l)                                      NumFluxes.jl:109-111
+__device__ __forceinline__ double hll_qhll(double a, double b, double Fa, double Fb, double acc, double s_l, double s_r, double inv_ds) {
+  const double path = (acc + Fb) - Fa;
+  return __dmul_rn(fma(b, s_r, -__dmul_rn(a, s_l)) - path, inv_ds);
+}
+//   D- = -s_l/(s_r-s_l) [F_r - F_l + B_int(Q_l,Q_hll) + B_int(Q_hll,Q_r)] + s_l s_r/(s_r-s_l) (Q_r - Q_l),  D+ likewise   :128-129
+__device__ __forceinline__ void hll_fluct(double a, double b, double Fa, double Fb, double acc, double k_q, double k_m, double k_p,
+                                          double& dm, double& dp) {
+  const double br = (Fb - Fa) + acc;
+  const double dq = __dmul_rn(k_q, b - a);
+  dm = fma(k_m, br, dq);
+  dp = fma(k_p, br, -dq);
+}
+//   (F(Q_l) + F(Q_r))/2 - lambda (Q_r - Q_l)/2                                                             NumFluxes.jl:30
+__device__ __forceinline__ double lxf_cons(double a, double b, double Fa, double Fb, double lambda) {
+  return fma(-(0.5 * lambda), b - a, 0.5 * (Fa + Fb));
+}
+//   Q - dt/dx ((F_r - F_l) + (NF_r + NF_l)) with the face terms already combined per side                  main.jl:59 / :40
+__device__ __forceinline__ double cell_update(double q, double upd, double from_right_face, double from_left_face) {
+  return fma(-upd, from_right_face + from_left_face, q);
+}
+
+// HLL wave-speed bounds of a face, NumFluxes.jl:86-91: min / max over 0, the speeds at Q_m = (Q_l + Q_r)/2 and the cached
+// bounds of the left / right cell.  a, b: record columns (row stride T).
+template <int MODEL, bool GEN, int T>
+__device__ __forceinline__ void face_speeds(const EosDev& eos, const double* a, const double* b, double lo_l, double hi_r,
+                                            double& s_l, double& s_r, int& bad) {
+  constexpr bool MPH = MODEL == MODEL_MPH30;
+  double m[3], A[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) m[k] = a[(2 + k) * T] + b[(2 + k) * T];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) A[k] = a[(6 + k) * T] + b[(6 + k) * T];
+  const double alpha = MPH ? 0.5 * (a[0] + b[0]) : 1.0;
+  PhaseState sm;   // (m, E, A are the sums: phase_state folds the halving in, exactly)
+  phase_state<GEN, !MPH, true, true>(eos, alpha, m, a[5 * T] + b[5 * T], A, sm);
+  bad |= sm.bad;
+  const double cm = phase_cmax<true>(eos, sm);
+  double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
+  if (MPH) {
+    lo_m = fmin(lo_m, __shfl_xor_sync(FULL, lo_m, 1));
+    hi_m = fmax(hi_m, __shfl_xor_sync(FULL, hi_m, 1));
+  }
+  s_l = fmin(0.0, fmin(lo_m, lo_l));
+  s_r = fmax(0.0, fmax(hi_m, hi_r));
 }
 
 // One face between the records in columns a (left) and b (right) with their physical fluxes Fa, Fb.
@@ -221,27 +296,8 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
   constexpr int J0 = ModelTraits<MODEL>::J0;
   constexpr bool MPH = MODEL == MODEL_MPH30;
   if (FLUX == FLUX_HLL) {
-    // wave-speed bounds at Q_m = (Q_l + Q_r)/2, NumFluxes.jl:86-91
     double s_l, s_r;
-    {
-      double m[3], A[9];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) m[k] = a[(2 + k) * T] + b[(2 + k) * T];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) A[k] = a[(6 + k) * T] + b[(6 + k) * T];
-      const double alpha = MPH ? 0.5 * (a[0] + b[0]) : 1.0;
-      PhaseState sm;   // (m, E, A are the sums: phase_state folds the halving in, exactly)
-      phase_state<GEN, !MPH, true, true>(eos, alpha, m, a[5 * T] + b[5 * T], A, sm);
-      bad |= sm.bad;
-      const double cm = phase_cmax<true>(eos, sm);
-      double lo_m = sm.u[0] - cm, hi_m = sm.u[0] + cm;
-      if (MPH) {
-        lo_m = fmin(lo_m, __shfl_xor_sync(FULL, lo_m, 1));
-        hi_m = fmax(hi_m, __shfl_xor_sync(FULL, hi_m, 1));
-      }
-      s_l = fmin(0.0, fmin(lo_m, lo_l));
-      s_r = fmax(0.0, fmax(hi_m, hi_r));
-    }
+    face_speeds<MODEL, GEN, T>(eos, a, b, lo_l, hi_r, s_l, s_r, bad);
     if (s_out) { s_out[0] = s_l; s_out[1] = s_r; }
     const double inv_ds = hs_rcp(s_r - s_l);
     const double k_q = s_l * s_r * inv_ds;
@@ -257,8 +313,7 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
 #pragma unroll
       for (int j = 0; j < 15; ++j) {
         if (j == 1) continue;
-        const double path = (acc[j] + HS_FLUX(Fb, j)) - HS_FLUX(Fa, j);                         // :109
-        const double qh = ((b[j * T] * s_r - a[j * T] * s_l) - path) * inv_ds;        // :111  Q_hll
+        const double qh = hll_qhll(a[j * T], b[j * T], HS_FLUX(Fa, j), HS_FLUX(Fb, j), acc[j], s_l, s_r, inv_ds);   // :109-111  Q_hll
         H[j * T] = qh - a[j * T];
         acc[j] = 0.0;
       }
@@ -270,9 +325,9 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
       const double k_m = -s_l * inv_ds, k_p = s_r * inv_ds;
 #pragma unroll
       for (int j = 0; j < 15; ++j) {                                                   // :128-129
-        const double br = (HS_FLUX(Fb, j) - HS_FLUX(Fa, j)) + (j == 1 ? 0.0 : acc[j]);
-        const double dq = k_q * (b[j * T] - a[j * T]);
-        emit(j, 0.0, k_m * br + dq, k_p * br - dq);
+        double dm, dp;
+        hll_fluct(a[j * T], b[j * T], HS_FLUX(Fa, j), HS_FLUX(Fb, j), j == 1 ? 0.0 : acc[j], k_q, k_m, k_p, dm, dp);
+        emit(j, 0.0, dm, dp);
       }
     } else {
       const double w_l = s_r * inv_ds, w_r = s_l * inv_ds;                             // weights of F_l and F_r
@@ -292,7 +347,7 @@ __device__ __forceinline__ void face_eval(const EosDev& eos, const double* a, co
     }
 #pragma unroll
     for (int j = J0; j < 15; ++j) {
-      const double cons = 0.5 * (HS_FLUX(Fa, j) + HS_FLUX(Fb, j)) - 0.5 * lambda * (b[j * T] - a[j * T]);  // :30
+      const double cons = lxf_cons(a[j * T], b[j * T], HS_FLUX(Fa, j), HS_FLUX(Fb, j), lambda);          // :30
       const double d = (MPH && j != 1) ? 0.5 * acc[j] : 0.0;                                       // :50-51
       emit(j, cons, d, d);
     }
@@ -307,7 +362,8 @@ struct StepArgs {
   double* tt;                // [3][nprob] time
   long long* steps;          // [nprob]
   int* status;
-  double* dt_hist; long long hist_k, hist_cap;   // dt_hist[prob*hist_cap + hist_k]
+  double* dt_hist; long long hist_k, hist_cap;   // dt_hist[prob*hist_cap + hist_k];  hist_k < 0: index from the device counter hist_n[prob]
+  long long* hist_n;         // [nprob] per-problem count of recorded steps (lets a captured CUDA graph of steps be replayed)
   long long stride;
   int ncells, nprob, tiles_per_prob;
   int cur, nxt, clr;
@@ -316,6 +372,14 @@ struct StepArgs {
   unsigned long long spin_ns;   // time limit of the tile-copy wait of k_step_sp (never hang the GPU on a lost copy)
   EosPair eos;
 };
+
+// dt of the step just taken by problem `prob` into the history (called by one thread per problem and step)
+__device__ __forceinline__ void hist_record(const StepArgs& g, int prob, double dt) {
+  if (!g.dt_hist) return;
+  long long k = g.hist_k;
+  if (k < 0) { k = g.hist_n[prob]; g.hist_n[prob] = k + 1; }
+  if (k < g.hist_cap) g.dt_hist[(size_t)prob * g.hist_cap + k] = dt;
+}
 
 // rows J0..14 of the record and scratch tiles, the non-zero flux rows, cached bounds, reduction scratch
 template <int MODEL, int T> constexpr size_t step_smem_bytes() {
@@ -479,7 +543,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     for (int j = J0; j < 15; ++j) {
       const double q = Rs[j * T + tid];
       const double mine = (MODEL == MODEL_MPH30) ? CR[j] : -Hs[j * T + tid];
-      qn[j] = own_interior ? q - upd * (Hs[j * T + tr] + mine) : q;
+      qn[j] = own_interior ? cell_update(q, upd, Hs[j * T + tr], mine) : q;
     }
     if (own_interior) {
       if (MODEL == MODEL_MPH30) {
@@ -541,10 +605,250 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
     if (tile == 0) {
       g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur + dt;   // main.jl:214
       g.steps[prob] += 1;                                   // main.jl:215
-      if (g.dt_hist && g.hist_k < g.hist_cap) g.dt_hist[(size_t)prob * g.hist_cap + g.hist_k] = dt;
+      hist_record(g, prob, dt);
       g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_step_qp: the two-phase time step for SMALL grids, quadrature-parallel.
+//
+// k_step gives every (cell, phase) one thread that walks through the 18 quadrature states of its face one after the other
+// (~6 300 dependent-ish instructions): on a grid that cannot fill the GPU -- the run main.jl ships is nx = 1000 -- the step time
+// is that thread's latency (~10 us), not throughput.  Here a block of 12 warps owns a tile of 16 cells (32 (cell, phase) pairs =
+// the 32 lanes of a warp, same lane layout as k_step: the other phase sits in lane ^ 1) and the independent pieces of a face run
+// in DIFFERENT WARPS at the same time:
+//   A   warps 0-5: quadrature node q = warp of B_int(Q_l, Q_r);  warp 6: physical flux of the cells;  warp 7: wave speeds at Q_m
+//   B   all warps: Q_hll from the six node terms (components shared out over the warps)
+//   C   warps 0-5: node q of B_int(Q_l, Q_hll);  warps 6-11: node q of B_int(Q_hll, Q_r)
+//   D   all warps: fluctuations D-, D+        E   all warps: conservative update        F   warp 0: CFL sweep of the new state
+// so the critical path is ~3 state evaluations + 2 eigen-solves instead of 20.  The node terms are handed over as (factor, value)
+// pairs and accumulated with the same fused multiply-adds in the same order as k_step's loop, and every other formula is the
+// shared inline function k_step uses: the result is BIT-IDENTICAL to k_step (tests/test_gpu_small_grid.py), so which kernel runs
+// is purely a matter of grid size (hsd_step: two-phase grids of <= HS_QP_MAX_CELLS cells, default 2048).
+// ------------------------------------------------------------------------------------------------
+constexpr int QP_NP = 32, QP_CPB = 16, QP_WARPS = 12, QP_T = QP_WARPS * 32;
+constexpr size_t qp_smem_doubles() {
+  return (size_t)QP_NP * (15 /*Rs*/ + 11 /*Fs*/ + 15 + 15 /*H1 H2*/ + 12 * 6 /*PF*/ + 12 * 14 /*PX*/ + 15 + 15 /*Hm CR*/ + 15 /*Rn*/ + 4 /*lo hi sl sr*/) + 32;
+}
+
+// one quadrature node: state of this lane's phase at base + s delta, the 6 factors and 14 values of w * (non-conservative column)
+template <bool GEN>
+__device__ __forceinline__ int qp_node(const EosDev& eos, const double* b14, const double* d14, double s, double w_q, double* PFq,
+                                       double* PXq, int lane) {
+  PhaseState st;
+  double A[9];
+  path_point<GEN>(eos, b14, d14, s, st, A);
+  NcTerms t;
+  noncons_terms(st, A, w_q * d14[0], t);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) PFq[k * QP_NP + lane] = t.f[k];
+#pragma unroll
+  for (int k = 0; k < 14; ++k) PXq[k * QP_NP + lane] = t.X[k];
+  return st.bad;
+}
+
+template <int FLUX, bool GEN, bool SAME>
+__global__ void __launch_bounds__(QP_T, 1) k_step_qp(const StepArgs g) {
+  constexpr int T = QP_NP, CPB = QP_CPB;   // (T: row stride of the shared tiles, as the HS_FLUX macro expects)
+  extern __shared__ double smem[];
+  double* Rs = smem;                 // records              [15][32]
+  double* Fs = Rs + 15 * T;          // physical flux        [11][32]  (flux_row)
+  double* H1 = Fs + 11 * T;          // Q_hll - Q_l          [15][32]
+  double* H2 = H1 + 15 * T;          // Q_r - Q_hll          [15][32]
+  double* PF = H2 + 15 * T;          // node factors         [12][6][32]
+  double* PX = PF + 12 * 6 * T;      // node values          [12][14][32]
+  double* Hm = PX + 12 * 14 * T;     // face term handed to the left cell  [15][32]
+  double* CR = Hm + 15 * T;          // face term kept by the right cell   [15][32]
+  double* Rn = CR + 15 * T;          // new records          [15][32]
+  double* lo_s = Rn + 15 * T;        // [16] cached bounds
+  double* hi_s = lo_s + T;
+  double* sl_s = hi_s + T;           // [32] s_l, s_r of this pair's face
+  double* sr_s = sl_s + T;
+  double* sc = sr_s + T;             // scalars
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int l = lane >> 1, ph = lane & 1;
+  const int prob = blockIdx.x / g.tiles_per_prob, tile = blockIdx.x % g.tiles_per_prob;
+  const int c = tile * (CPB - 2) + l;
+  const bool valid = c < g.ncells;
+  const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
+  const EosDev& eos = g.eos.e[SAME ? 0 : ph];
+
+  for (int j = warp; j < 15; j += QP_WARPS) Rs[j * T + lane] = __ldg(g.Qin + (size_t)(15 * ph + j) * g.stride + gi);
+  if (warp == QP_WARPS - 1 && ph == 0) { lo_s[l] = __ldg(g.aux_in + gi); hi_s[l] = __ldg(g.aux_in + g.stride + gi); }
+  if (tid == 0) {
+    const unsigned long long lam_bits = __ldg(g.lam + (size_t)g.cur * g.nprob + prob);
+    const double lam_cur = __longlong_as_double((long long)lam_bits);
+    const double dt0 = g.cfl * g.dx / lam_cur;           // main.jl:212
+    const double lambda0 = g.dx / dt0;                   // main.jl:223
+    sc[0] = dt0;
+    sc[1] = (FLUX == FLUX_HLL) ? dt0 / g.dx : 1.0 / lambda0;   // main.jl:225,59 / :40
+    sc[2] = lambda0;
+    sc[3] = __ldg(g.tt + (size_t)g.cur * g.nprob + prob);
+    sc[4] = lam_cur;
+  }
+  __syncthreads();
+  const double dt = sc[0], upd = sc[1], lambda = sc[2], t_cur = sc[3];
+  const bool active = t_cur < g.t_end;                   // while t < T, main.jl:202
+  const bool own_interior = valid && l >= 1 && l <= CPB - 2 && c <= g.ncells - 2;
+  const bool own_frozen = valid && ((c == 0 && !(g.ghost & 1)) || (c == g.ncells - 1 && !(g.ghost & 2)));
+  if (!active) {  // this problem already reached t_end: carry the state through unchanged
+    if (own_interior || own_frozen) {
+      for (int j = warp; j < 15; j += QP_WARPS) g.Qout[(size_t)(15 * ph + j) * g.stride + gi] = Rs[j * T + lane];
+      if (warp == QP_WARPS - 1 && ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
+    }
+    if (tile == 0 && tid == 0) {
+      g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur;
+      g.lam[(size_t)g.nxt * g.nprob + prob] = (unsigned long long)__double_as_longlong(sc[4]);
+      g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
+    }
+    return;
+  }
+
+  const int tl = (l >= 1) ? lane - 2 : lane;   // the face of pair `lane` lies between cell l-1 and cell l (l = 0: dummy face)
+  const double* a = Rs + tl;
+  const double* b = Rs + lane;
+  const double* Fa = Fs + tl;
+  const double* Fb = Fs + lane;
+  const double* xs = (FLUX == FLUX_HLL) ? c_gleg_x : c_glob_x;
+  const double* ws = (FLUX == FLUX_HLL) ? c_gleg_w : c_glob_w;
+  int bad = 0;
+
+  // ---- A: first path integral (one node per warp) | physical flux | wave speeds at Q_m ---------------------------------
+  if (warp < 6) {
+    double b14[14], d14[14];
+    b14[0] = a[0]; d14[0] = b[0] - a[0];
+#pragma unroll
+    for (int k = 1; k < 14; ++k) { b14[k] = a[(1 + k) * T]; d14[k] = b[(1 + k) * T] - a[(1 + k) * T]; }
+    const int nb = qp_node<GEN>(eos, b14, d14, xs[warp], ws[warp], PF + warp * 6 * T, PX + warp * 14 * T, lane);
+    if (valid && l >= 1) bad |= nb;
+  } else if (warp == 6) {
+    PhaseState st;
+    column_state<MODEL_MPH30, GEN, T>(eos, Rs + lane, st);
+    if (valid) bad |= st.bad;
+    double A[9], f[15];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A[k] = Rs[(6 + k) * T + lane];
+    phase_flux(st, A, f);
+#pragma unroll
+    for (int j = 1; j < 15; ++j)
+      if (!flux_is_zero(j)) Fs[flux_row(j) * T + lane] = f[j];
+  } else if (warp == 7 && FLUX == FLUX_HLL) {
+    double s_l, s_r;
+    int fbad = 0;
+    face_speeds<MODEL_MPH30, GEN, T>(eos, a, b, lo_s[(l >= 1) ? l - 1 : l], hi_s[l], s_l, s_r, fbad);
+    sl_s[lane] = s_l; sr_s[lane] = s_r;
+    if (valid && l >= 1) bad |= fbad;
+  }
+  __syncthreads();
+
+  if (FLUX == FLUX_HLL) {
+    const double s_l = sl_s[lane], s_r = sr_s[lane];
+    const double inv_ds = hs_rcp(s_r - s_l);
+    // ---- B: Q_hll (NumFluxes.jl:109-111) and the deltas of the two remaining segments ------------------------------------
+    for (int k = warp; k < 14; k += QP_WARPS) {
+      const int j = nc_slot(k), fk = nc_factor(k);
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc = fma(PF[(q * 6 + fk) * T + lane], PX[(q * 14 + k) * T + lane], acc);
+      const double qh = hll_qhll(a[j * T], b[j * T], HS_FLUX(Fa, j), HS_FLUX(Fb, j), acc, s_l, s_r, inv_ds);
+      const double h1 = qh - a[j * T];
+      H1[j * T + lane] = h1;
+      H2[j * T + lane] = (b[j * T] - a[j * T]) - h1;
+    }
+    __syncthreads();
+    // ---- C: B_int(Q_l, Q_hll) in warps 0-5, B_int(Q_hll, Q_r) in warps 6-11 -----------------------------------------------
+    {
+      const bool second = warp >= 6;
+      const int q = second ? warp - 6 : warp;
+      const double* base = second ? b : a;
+      const double* dl = (second ? H2 : H1) + lane;
+      double b14[14], d14[14];
+      b14[0] = base[0]; d14[0] = dl[0];
+#pragma unroll
+      for (int k = 1; k < 14; ++k) { b14[k] = base[(1 + k) * T]; d14[k] = dl[(1 + k) * T]; }
+      const int nb = qp_node<GEN>(eos, b14, d14, second ? xs[q] - 1.0 : xs[q], ws[q], PF + warp * 6 * T, PX + warp * 14 * T, lane);
+      if (valid && l >= 1) bad |= nb;
+    }
+    __syncthreads();
+    // ---- D: fluctuations (NumFluxes.jl:128-129) -----------------------------------------------------------------------------
+    const double k_q = s_l * s_r * inv_ds, k_m = -s_l * inv_ds, k_p = s_r * inv_ds;
+    for (int j = warp; j < 15; j += QP_WARPS) {
+      double acc = 0.0;
+      if (j != 1) {
+        const int k = j == 0 ? 0 : j - 1, fk = nc_factor(k);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) acc = fma(PF[(q * 6 + fk) * T + lane], PX[(q * 14 + k) * T + lane], acc);
+      }
+      double dm, dp;
+      hll_fluct(a[j * T], b[j * T], HS_FLUX(Fa, j), HS_FLUX(Fb, j), acc, k_q, k_m, k_p, dm, dp);
+      Hm[j * T + lane] = 0.0 + dm;      // F_r + NF_r of the left cell  (update_cell, main.jl:57-59; hll's conservative part is zero)
+      CR[j * T + lane] = dp - 0.0;      // - F_l + NF_l of this cell
+    }
+  } else {
+    // ---- D (LxF): NumFluxes.jl:30, :50-51 ---------------------------------------------------------------------------------
+    for (int j = warp; j < 15; j += QP_WARPS) {
+      double acc = 0.0;
+      if (j != 1) {
+        const int k = j == 0 ? 0 : j - 1, fk = nc_factor(k);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc = fma(PF[(q * 6 + fk) * T + lane], PX[(q * 14 + k) * T + lane], acc);
+      }
+      const double cons = lxf_cons(a[j * T], b[j * T], HS_FLUX(Fa, j), HS_FLUX(Fb, j), lambda);
+      const double d = (j != 1) ? 0.5 * acc : 0.0;
+      Hm[j * T + lane] = cons + d;
+      CR[j * T + lane] = d - cons;
+    }
+  }
+  __syncthreads();
+
+  // ---- E: conservative update (update_cell, main.jl:59 / :40) -------------------------------------------------------------
+  {
+    const int tr = own_interior ? lane + 2 : lane;
+    for (int j = warp; j < 15; j += QP_WARPS) {
+      const double q = Rs[j * T + lane];
+      const double qn = own_interior ? cell_update(q, upd, Hm[j * T + tr], CR[j * T + lane]) : q;
+      Rn[j * T + lane] = qn;
+      if (own_interior || own_frozen) g.Qout[(size_t)(15 * ph + j) * g.stride + gi] = qn;
+    }
+  }
+  __syncthreads();
+
+  // ---- F: CFL sweep of the next step on the state just produced (get_eigvals, main.jl:204-211) ----------------------------
+  if (warp == 0) {
+    double qn[15];
+#pragma unroll
+    for (int j = 0; j < 15; ++j) qn[j] = Rn[j * T + lane];
+    PhaseState sn;
+    phase_state<GEN, false, true>(eos, qn[0], qn + 2, qn[5], qn + 6, sn);
+    const double cn = phase_cmax<true>(eos, sn);
+    double lo_n = sn.u[0] - cn, hi_n = sn.u[0] + cn;
+    lo_n = fmin(lo_n, __shfl_xor_sync(FULL, lo_n, 1));
+    hi_n = fmax(hi_n, __shfl_xor_sync(FULL, hi_n, 1));
+    double lamv = 0.0;
+    if (own_interior) {
+      bad |= sn.bad;
+      if (ph == 0) { g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n; }
+      lamv = fmax(fabs(lo_n), fabs(hi_n));
+    } else if (own_frozen) {
+      if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
+      lamv = fmax(fabs(lo_s[l]), fabs(hi_s[l]));
+    }
+    lamv = warp_max_nonneg(lamv);
+    if (lane == 0) {
+      atomicMax(g.lam + (size_t)g.nxt * g.nprob + prob, (unsigned long long)__double_as_longlong(lamv));
+      if (tile == 0) {
+        g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur + dt;   // main.jl:214
+        g.steps[prob] += 1;                                   // main.jl:215
+        hist_record(g, prob, dt);
+        g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
+      }
+    }
+  }
+  bad = __any_sync(FULL, bad);
+  if (bad && lane == 0) atomicOr(g.status, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -886,7 +1190,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       if (tile == 0 && tid == 0) {
         g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur + dt;   // main.jl:214
         g.steps[prob] += 1;                                   // main.jl:215
-        if (g.dt_hist && g.hist_k < g.hist_cap) g.dt_hist[(size_t)prob * g.hist_cap + g.hist_k] = dt;
+        hist_record(g, prob, dt);
         g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
       }
     }

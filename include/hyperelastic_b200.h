@@ -204,7 +204,11 @@ int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa_dev, double* aos_de
 /* CFL sweep: fills aux and lambda_max slot `slot` of scal (after zeroing it) */
 int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot, void* stream);
 /* one fused step n: reads Qin/aux_in and slot n%3, writes Qout/aux_out and slot (n+1)%3;
- * if dt_hist != NULL the step's dt of problem p is stored at dt_hist[p*hist_cap + hist_k].
+ * if dt_hist != NULL the step's dt of problem p is stored at dt_hist[p*hist_cap + hist_k] (hist_k < 0: at the index the
+ * per-problem counter inside `scal` holds, which the kernel then increments -- what lets a captured CUDA graph of steps be replayed).
+ * Two-phase grids of at most HS_QP_MAX_CELLS cells (environment, default 2048; 0 = never) are stepped by the quadrature-parallel
+ * kernel k_step_qp (one warp per quadrature node: low latency on grids too small to fill the GPU); its results are bit-identical
+ * to the fused kernel's, so the switch is invisible.
  * ghost_mask bit 0 / bit 1: the first / last cell of the array is a halo copy of a neighbouring
  * slab's cell (not written, not counted in lambda_max) instead of a frozen physical boundary cell
  * (main.jl:219-220). */
