@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("HYPERELASTIC_B200_LIB") or os.path.join(_HERE, "libhyperelastic_b200.so")  # env override: tuning builds
 CSRC = os.path.join(_HERE, "csrc")
 
-HS_OK, HS_ERR_ARG, HS_ERR_CUDA, HS_ERR_DOMAIN, HS_ERR_NCCL = 0, 1, 2, 3, 4
+HS_OK, HS_ERR_ARG, HS_ERR_CUDA, HS_ERR_DOMAIN, HS_ERR_EXCHANGE = 0, 1, 2, 3, 4
 SP13, MPH30 = 0, 1
 LXF, HLL = 0, 1
 NVAR = {SP13: 13, MPH30: 30}

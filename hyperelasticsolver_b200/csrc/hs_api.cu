@@ -572,7 +572,7 @@ static int read_status(hs_ctx* c) {
     CU(cudaStreamSynchronize(p.stream));
     bad |= st;
   }
-  if (bad & 2) return fail(HS_ERR_CUDA, "peer-memory exchange timed out: a device of the context stopped stepping");
+  if (bad & 2) return fail(HS_ERR_EXCHANGE, "peer-memory exchange timed out: a device of the context stopped stepping");
   if (bad & 4) return fail(HS_ERR_CUDA, "tile copy (TMA) did not complete: internal error of the single-phase step kernel");
   if (bad) return fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError");
   return HS_OK;

@@ -132,7 +132,7 @@ class _Base:
     def check_status(self):
         st = int(self._status.cpu()[0])
         if st & 2:
-            raise L.HyperelasticError(L.HS_ERR_CUDA, "peer-memory exchange timed out: another rank stopped stepping")
+            raise L.HyperelasticError(L.HS_ERR_EXCHANGE, "peer-memory exchange timed out: another rank stopped stepping")
         if st & 4:
             raise L.HyperelasticError(L.HS_ERR_CUDA, "tile copy (TMA) did not complete: internal error of the single-phase step kernel")
         if st != 0:

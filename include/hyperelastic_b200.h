@@ -31,7 +31,10 @@
 extern "C" {
 #endif
 
-enum { HS_OK = 0, HS_ERR_ARG = 1, HS_ERR_CUDA = 2, HS_ERR_DOMAIN = 3, HS_ERR_NCCL = 4 };
+/* HS_ERR_EXCHANGE: the multi-GPU halo / max(lambda) exchange of a slab-decomposed grid did not complete (a peer stopped stepping:
+ * the exchange kernel gave up after HS_EXCHANGE_TIMEOUT_S seconds instead of hanging the GPU).  The library itself never calls
+ * NCCL: the one-process-per-GPU driver (hyperelasticsolver_b200/slab.py) may, as its fallback exchange, through torch.distributed. */
+enum { HS_OK = 0, HS_ERR_ARG = 1, HS_ERR_CUDA = 2, HS_ERR_DOMAIN = 3, HS_ERR_EXCHANGE = 4 };
 enum { HS_MODEL_SP13 = 0, HS_MODEL_MPH30 = 1 };
 enum { HS_FLUX_LXF = 0, HS_FLUX_HLL = 1 };
 

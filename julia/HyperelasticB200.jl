@@ -23,7 +23,7 @@ export Barton2009, Hank2016, energy, pressure, stress, prim2cons_mph, cons2prim_
 
 const LIB = get(ENV, "HYPERELASTIC_B200_LIB", joinpath(@__DIR__, "..", "hyperelasticsolver_b200", "libhyperelastic_b200.so"))
 
-const HS_OK, HS_ERR_ARG, HS_ERR_CUDA, HS_ERR_DOMAIN = 0, 1, 2, 3
+const HS_OK, HS_ERR_ARG, HS_ERR_CUDA, HS_ERR_DOMAIN, HS_ERR_EXCHANGE = 0, 1, 2, 3, 4
 const HS_MODEL_SP13, HS_MODEL_MPH30 = 0, 1
 const HS_FLUX_LXF, HS_FLUX_HLL = 0, 1
 

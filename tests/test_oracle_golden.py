@@ -268,3 +268,71 @@ def test_wave_speeds_rotate_with_the_frame(oracle):
         e1, st1 = oracle.get_eigvals(None, 1, qr[None])
         assert st == 0 and st1 == 0
         assert np.abs(en - e1).max() < 1e-12 * np.abs(e1).max()
+
+
+def test_oracle_within_roundoff_of_exact_arithmetic(oracle):
+    """oracle/mporacle.py evaluates the reference's formulas in 50-digit arithmetic (nested dual numbers over mpmath):
+    tests/golden/mp_vectors.json holds cons2prim / flux / acoustic tensor / eigvals / non-conservative columns of the 24
+    golden phase states and two complete path-conservative HLL faces to 30 digits.  The FP64 C++ oracle must sit within
+    a few 1e-15 of them (1e-14 .. 1e-13 where the reference's own formula cancels: flux differences, S = cv log(1 +
+    (e - ...)/(cv t0 ...))): this bounds the oracle's roundoff ~100x below the 1e-12 parity tolerance of the GPU tests."""
+    d = json.load(open(os.path.join(G, "mp_vectors.json")))
+    f = lambda L: np.array([float(x) for x in L])
+    rel = lambda a, b: np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max()
+    assert len(d["cases"]) == 12
+    for c in d["cases"]:
+        eos = [np.array(b) for b in c["eos_blocks"]]
+        Q = np.array(c["Q"])
+        P = oracle.cons2prim(eos, 1, Q)[0]
+        Pm = f(c["cons2prim"])
+        assert rel(P, Pm) < 5e-15
+        for k in (5, 20):
+            assert abs(P[k] - Pm[k]) < 1e-13 * abs(Pm[k])          # entropy: roundoff of e_int amplified by 1/(cv t0)
+        assert rel(oracle.flux(eos, 1, Q)[0], f(c["flux"])) < 1e-13
+        assert rel(oracle.get_eigvals(eos, 1, Q)[0][0], f(c["eigvals"])) < 1e-14
+        assert rel(oracle.noncons_cols(eos, Q)[0], f(c["noncons_cols"])) < 5e-14
+        for p in range(2):
+            ac = oracle.acoustic(eos[p], P[15 * p + 5], P[15 * p + 6:15 * p + 15])
+            am = np.array([[float(x) for x in row] for row in c["acoustic"][p]])
+            assert np.abs(ac - am).max() < 2e-14 * np.abs(am).max()
+            assert np.abs(am - am.T).max() < 1e-28 * np.abs(am).max()      # symmetric in exact arithmetic (30 digits stored)
+    for fc in d["hll_faces"]:
+        eos = [np.array(b) for b in fc["eos_blocks"]]
+        Ql, Qr = np.array(fc["Ql"]), np.array(fc["Qr"])
+        el, _ = oracle.get_eigvals(eos, 1, Ql[None]); er, _ = oracle.get_eigvals(eos, 1, Qr[None])
+        _, dm, dp, s, st = oracle.hll(eos, Ql[None], Qr[None], el, er)
+        assert st == 0
+        assert abs(s[0][0] - float(fc["s_l"])) < 5e-15 * abs(s[0][0]) and abs(s[0][1] - float(fc["s_r"])) < 5e-15 * abs(s[0][1])
+        assert rel(dm[0], f(fc["dm"])) < 1e-14 and rel(dp[0], f(fc["dp"])) < 1e-14
+    x, w = oracle.quadrature(False)
+    assert np.abs(x - f(d["gauss_legendre6"]["x"])).max() < 1e-16 and np.abs(w - f(d["gauss_legendre6"]["w"])).max() < 1e-16
+
+
+def test_mp_restatement_anchors():
+    """the arbitrary-precision restatement itself, on facts that need no other implementation: zero stress, T = t0 and speeds
+    (b0, b0, c0) at F = I, S = 0 to 40 digits; derivative identities; regenerating one stored case reproduces the file"""
+    import importlib.util
+    import mpmath as mp
+    spec = importlib.util.spec_from_file_location("mporacle", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "mporacle.py"))
+    M = importlib.util.module_from_spec(spec); spec.loader.exec_module(M)
+    blk = [8.93, 4.6, 3.9e-4, 300.0, 2.1, 1.0, 3.0, 2.0, 2.1 ** 2, 4.6 ** 2 - (4 / 3) * 2.1 ** 2]
+    eos = M.Barton2009(blk)
+    I9 = [mp.mpf(x) for x in (1, 0, 0, 0, 1, 0, 0, 0, 1)]
+    assert max(abs(x) for x in M.stress(eos, mp.mpf(0), I9)) < mp.mpf("1e-40")
+    T = M.energy(eos, M.Dual(mp.mpf(0), mp.mpf(1)), M.finger(I9)).d
+    assert abs(T - eos.t0) < mp.mpf("1e-40")
+    ac = M.acoustic(eos, mp.mpf(0), I9)
+    ev = M.eig_sym3(ac)
+    # longitudinal speed^2 = k0 + 4/3 b0sq with the struct's (rounded) k0, b0sq; shear speed^2 = b0sq
+    assert abs(ev[2] - (eos.k0 + mp.mpf(4) / 3 * eos.b0sq)) < mp.mpf("1e-40") and abs(ev[0] - eos.b0sq) < mp.mpf("1e-40") and abs(ev[1] - eos.b0sq) < mp.mpf("1e-40")
+    # entropy inverts energy in S
+    F = [mp.mpf(x) for x in (0.98, 0.02, 0.0, 0.0, 1.0, 0.0, 0.0, 0.1, 1.0)]
+    Gf = M.finger(F)
+    S = mp.mpf("7.5e-4")
+    assert abs(M.entropy(eos, M.energy(eos, S, Gf), Gf) - S) < mp.mpf("1e-45")
+    d = json.load(open(os.path.join(G, "mp_vectors.json")))
+    c = d["cases"][7]
+    eoss = [M.Barton2009(b) for b in c["eos_blocks"]]
+    Q = [mp.mpf(float(x)) for x in c["Q"]]
+    again = [M.s30(x) for x in M.noncons_cols(eoss, Q)]
+    assert again == c["noncons_cols"]
