@@ -87,6 +87,29 @@ def workload_config(name, world):
             "l2": f"state {per_gpu * nvar * 8 / 1e9:.2f} GB per GPU per buffer >> 126 MB L2 (inputs larger than L2, no flush needed)"}
 
 
+def numa_local_affinity(dev_index):
+    """Bind this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers allocated next are
+    NUMA-local to its PCIe root (first-touch placement).  Returns the node, or None if it cannot be determined."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(dev_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus          # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -394,6 +417,7 @@ class Bench:
         from hyperelasticsolver_b200.slab import EnsembleSolver, SlabSolver
         wl, nvar, world, rank, kern = c["wl"], c["nvar"], self.world, self.rank, c["kern"]
         flux = L.HLL
+        numa = numa_local_affinity(self.local)      # pinned buffers below land on the GPU's own NUMA node
         if c["ensemble"]:
             nprob_e = min(wl["nprob"], (1 << 24) // wl["cells"] * world)
             pe0, pe1 = nprob_e * rank // world, nprob_e * (rank + 1) // world
@@ -413,12 +437,13 @@ class Bench:
                 s2 = H.Solver(c["eos"], e_cells, model=c["hmodel"], device=self.local)
                 e_cells_local, lo_g = e_cells, 0
                 step_host = lambda a, b: s2.step_host(a.numpy(), b.numpy(), "hll", 0.6, 1.0 / e_units)
-                api = "hs_step_host (C ABI): upload Q0 + CFL sweep + fused step + download Q1, every step"
+                api = "hs_step_host (C ABI): upload Q0 + CFL sweep + fused step + download Q1, every step, chunk-pipelined (H2D || kernels || D2H)"
             else:
                 sol = SlabSolver(kern, e_units)
                 e_cells_local, lo_g = sol.nloc, sol.lo_g
                 step_host = lambda a, b: sol.step_host(a, b, flux, 0.6, 1.0 / e_units)
-                api = "SlabSolver.step_host: pinned host slab -> device, CFL sweep + allreduce, fused step, halo, device -> host, every step"
+                api = ("SlabSolver.step_host: pinned host slab -> device, CFL sweep, fused step, exchange, device -> host, every step, "
+                       "chunk-pipelined over three streams per rank (speculative dt, confirmed by an all-reduce of the sweep's max(lambda))")
             host_in = torch.empty(e_cells_local, nvar, dtype=torch.float64, pin_memory=True)
             host_out = torch.empty_like(host_in).pin_memory()
             gi = torch.arange(lo_g, lo_g + e_cells_local)
@@ -437,7 +462,8 @@ class Bench:
         nbytes = e_units * nvar * 8
         return {"value": e_units * e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_t / e2e_steps, "cells_total": e_units, "api": api,
-                "gpu_launches_per_rank": kern.launches() - l0}
+                "gpu_launches_per_rank": kern.launches() - l0, "host_buffers": "pinned (torch), NUMA node of the GPU: " + str(numa),
+                "link_roof_note": "PCIe Gen5 x16 measured on this pool: 55.5 GB/s one direction alone, 48 GB/s each with both directions busy (profiles/r02_e2e_link_probe.log)"}
 
     # ---- correctness carried by the bench line -----------------------------------------------------------
     def parity_check(self):

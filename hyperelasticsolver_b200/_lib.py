@@ -98,6 +98,7 @@ SIGNATURES = {
     "hsd_aos_to_soa": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp]),
     "hsd_soa_to_aos": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp]),
     "hsd_wave_bounds": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, C.c_int, _vp]),
+    "hsd_wave_bounds_acc": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, C.c_int, _vp]),
     "hsd_step": (C.c_int, [C.POINTER(HsdProblem), C.c_int, C.c_double, C.c_double, C.c_double, _i64,
                            _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
     "hsd_halo": (C.c_int, [C.POINTER(HsdProblem), _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),

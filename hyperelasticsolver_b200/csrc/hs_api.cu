@@ -290,12 +290,13 @@ static int transpose_range(int model, bool to_soa, const double* src, double* ds
   return HS_OK;
 }
 
+// (ncells * nprob cells; for a WINDOW descriptor -- fewer cells than the row pitch `stride`, pointers into larger arrays -- only the window)
 int hsd_aos_to_soa(const hsd_problem_t* p, const double* aos, double* soa, void* stream) {
-  return transpose_range(p->model, true, aos, soa, p->stride, p->stride, (cudaStream_t)stream);
+  return transpose_range(p->model, true, aos, soa, p->ncells * p->nprob, p->stride, (cudaStream_t)stream);
 }
 
 int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa, double* aos, void* stream) {
-  return transpose_range(p->model, false, soa, aos, p->stride, p->stride, (cudaStream_t)stream);
+  return transpose_range(p->model, false, soa, aos, p->ncells * p->nprob, p->stride, (cudaStream_t)stream);
 }
 
 // accumulate: keep the slot's current value and max into it (the sweep of one window of a grid that arrives chunk by chunk)
@@ -324,6 +325,9 @@ static int wave_bounds_impl(const hsd_problem_t* p, const double* Q, double* aux
 
 int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot, void* stream) {
   return wave_bounds_impl(p, Q, aux, scal, slot, nullptr, (cudaStream_t)stream);
+}
+int hsd_wave_bounds_acc(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot, void* stream) {
+  return wave_bounds_impl(p, Q, aux, scal, slot, nullptr, (cudaStream_t)stream, true);
 }
 
 int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,

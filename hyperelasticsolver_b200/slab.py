@@ -80,8 +80,16 @@ class CudaKernels:
     def soa_to_aos(self, prob, soa, aos):
         L.check(self._lib.hsd_soa_to_aos(C.byref(prob), soa.data_ptr(), aos.data_ptr(), self._stream()))
 
-    def wave_bounds(self, prob, Q, aux, scal, slot):
-        L.check(self._lib.hsd_wave_bounds(C.byref(prob), Q.data_ptr(), aux.data_ptr(), scal.data_ptr(), slot, self._stream()))
+    def wave_bounds(self, prob, Q, aux, scal, slot, accumulate=False):
+        fn = self._lib.hsd_wave_bounds_acc if accumulate else self._lib.hsd_wave_bounds
+        L.check(fn(C.byref(prob), Q.data_ptr(), aux.data_ptr(), scal.data_ptr(), slot, self._stream()))
+
+    def window(self, prob, ncells):
+        """descriptor of a window of `ncells` cells of the grid `prob` describes (same row pitch): see WINDOWS in the header"""
+        w = L.HsdProblem()
+        C.memmove(C.byref(w), C.byref(prob), C.sizeof(L.HsdProblem))
+        w.ncells, w.nprob = int(ncells), 1
+        return w
 
     def step(self, prob, flux, cfl, dx, t_end, n, Qin, aux_in, Qout, aux_out, scal, ghost_mask, dt_hist=None, hist_k=0, hist_cap=0):
         L.check(self._lib.hsd_step(C.byref(prob), flux, cfl, dx, t_end, n, Qin.data_ptr(), aux_in.data_ptr(),
@@ -223,9 +231,9 @@ class SlabSolver(_Base):
         self.k.soa_to_aos(self.prob, self.Q[self.n & 1], aos)
         return aos.cpu().numpy()
 
-    def step_host(self, host_in, host_out, flux=L.HLL, cfl=0.6, dx=None):
+    def step_host_serial(self, host_in, host_out, flux=L.HLL, cfl=0.6, dx=None):
         """One step on host slabs (pinned torch tensors (nloc, nvar)): H2D, CFL sweep (+ allreduce),
-        fused step, halo, D2H -- the multi-GPU counterpart of the C ABI's hs_step_host."""
+        fused step, halo, D2H one after the other."""
         if not hasattr(self, "_stage"):
             self._stage = self.k.empty(self.nloc, self.nvar)
         self._stage.copy_(host_in, non_blocking=True)
@@ -234,6 +242,110 @@ class SlabSolver(_Base):
         self.k.soa_to_aos(self.prob, self.Q[self.n & 1], self._stage)
         host_out.copy_(self._stage, non_blocking=True)
         torch.cuda.current_stream(self.k.device).synchronize()
+        self._have_hint = True
+
+    def step_host(self, host_in, host_out, flux=L.HLL, cfl=0.6, dx=None, chunk=1 << 19):
+        """One step on host slabs, chunk-pipelined -- the multi-GPU counterpart of the C ABI's hs_step_host (see the header):
+        H2D of chunk i+1 || transpose + CFL sweep + fused step of chunk i (speculative dt from the GLOBAL max(lambda) the previous
+        call's exchange left in the scalar slot) || D2H of chunk i-1 on three streams; then the exchange (halo cells of the new
+        state, global max(lambda) of the new state) and one all-reduce(max) of the sweep's max(lambda), compared with the hint bit
+        for bit on every rank.  A refuted hint (first call, edited state) redoes the step on the device.  Results are bit-identical
+        to step_host_serial."""
+        import os
+        dx = 1.0 / self.n_global if dx is None else dx
+        N, nvar, dev = self.nloc, self.nvar, self.k.device
+        if os.environ.get("HS_HOST_PIPELINE", "1") == "0" or N % 2 or N < 4096 or not host_in.is_pinned() or not host_out.is_pinned():
+            return self.step_host_serial(host_in, host_out, flux, cfl, dx)
+        if not hasattr(self, "_pipe"):
+            self._stage = self.k.empty(N, nvar)
+            self._pipe = dict(out=self.k.empty(N, nvar), sweep=self.k.zeros(scal_size(1)), s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
+                              hint=self.k.zeros(1))
+        P = self._pipe
+        main = torch.cuda.current_stream(dev)
+        # chunk boundaries: short first chunks, then equal ones; all even (hs_step_host uses the same rule)
+        bnd, lo, sz = [], 0, max(chunk // 32, 2)
+        while sz < chunk and N - lo > 2 * chunk + 4 * sz:
+            bnd.append(lo); lo += sz & ~1; sz *= 2
+        bnd += list(range(lo, N, chunk))
+        if len(bnd) > 1 and N - bnd[-1] < chunk // 4:
+            bnd.pop()
+        bnd.append(N)
+        K = len(bnd) - 1
+        spec = bool(getattr(self, "_have_hint", False))
+        self._have_hint = False
+        if spec:
+            P["hint"].copy_(self._lam[self.n % 3])          # global max(lambda) of the state the previous call returned
+        self.scal.zero_(); P["sweep"].zero_()
+        self.n = 0
+        if spec:
+            self._lam[0].copy_(P["hint"])
+        start = torch.cuda.Event(); start.record(main)
+        P["s_in"].wait_event(start); P["s_out"].wait_event(start)
+        Q0, Q1, A0, A1 = self.Q[0], self.Q[1], self.aux[0], self.aux[1]
+        for i in range(K):
+            b0, b1 = bnd[i], bnd[i + 1]
+            with torch.cuda.stream(P["s_in"]):
+                self._stage[b0:b1].copy_(host_in[b0:b1], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(P["s_in"])
+            main.wait_event(ev)
+            w = self.k.window(self.prob, b1 - b0)
+            self.k.aos_to_soa(w, self._stage[b0:b1], Q0[:, b0:])
+            self.k.wave_bounds(w, Q0[:, b0:], A0[:, b0:], P["sweep"], 0, accumulate=True)
+            if spec:
+                w0 = b0 - 2 if i else 0
+                ghost = ((1 if i else (self.ghost_mask & 1)) | (2 if i < K - 1 else (self.ghost_mask & 2)))
+                ws = self.k.window(self.prob, b1 - w0)
+                self.k.step(ws, flux, cfl, dx, 1.0e300, 0, Q0[:, w0:], A0[:, w0:], Q1[:, w0:], A1[:, w0:], self.scal, ghost)
+                u0, u1 = (b0 - 1 if i else 0), (b1 - 1 if i < K - 1 else N)
+                wo = self.k.window(self.prob, u1 - u0)
+                self.k.soa_to_aos(wo, Q1[:, u0:], P["out"][u0:u1])
+                ev2 = torch.cuda.Event(); ev2.record(main)
+                P["s_out"].wait_event(ev2)
+                with torch.cuda.stream(P["s_out"]):
+                    host_out[u0:u1].copy_(P["out"][u0:u1], non_blocking=True)
+        lam_true = P["sweep"][0:1]
+        if self.world > 1:
+            dist.all_reduce(lam_true, op=dist.ReduceOp.MAX, group=self.group)
+        ok = spec and bool(torch.equal(lam_true.view(torch.int64), P["hint"].view(torch.int64)))   # (host sync; identical on all ranks)
+        self._status |= P["sweep"][L.HS_SCAL_SLOTS:L.HS_SCAL_SLOTS + 1].view(torch.int32)
+        if not ok:
+            P["s_out"].synchronize()
+            st = self._status.clone()
+            self.scal.zero_(); self._status.copy_(st)
+            self._lam[0].copy_(lam_true)
+            self.n = 0
+            self.step(flux, cfl, dx)                       # fused step + exchange from the intact input
+            for i in range(K):
+                b0, b1 = bnd[i], bnd[i + 1]
+                wo = self.k.window(self.prob, b1 - b0)
+                self.k.soa_to_aos(wo, Q1[:, b0:], P["out"][b0:b1])
+                ev2 = torch.cuda.Event(); ev2.record(main)
+                P["s_out"].wait_event(ev2)
+                with torch.cuda.stream(P["s_out"]):
+                    host_out[b0:b1].copy_(P["out"][b0:b1], non_blocking=True)
+        else:
+            # every window counted a step; the grid took one.  Then what step() does after the kernel: halo cells + global max(lambda)
+            self._steps.fill_(1)
+            if self.exchange == "p2p-kernel":
+                self._xseq += 1
+                self.k.exchange_p2p(self.prob, Q1, A1, self._lam[1], self._peer_ptrs, self.rank, self.world, self._xseq, self.scal)
+            else:
+                self._halo_exchange(1)
+                self._allreduce_lambda(1)
+            self.n = 1
+            if self.ghost_mask:   # the halo cells of the new state arrived with the exchange: send them after the chunks
+                for u0, u1 in ((0, 2), (N - 2, N)):
+                    wo = self.k.window(self.prob, 2)
+                    self.k.soa_to_aos(wo, Q1[:, u0:], P["out"][u0:u1])
+                ev2 = torch.cuda.Event(); ev2.record(main)
+                P["s_out"].wait_event(ev2)
+                with torch.cuda.stream(P["s_out"]):
+                    host_out[0:2].copy_(P["out"][0:2], non_blocking=True)
+                    host_out[N - 2:N].copy_(P["out"][N - 2:N], non_blocking=True)
+        main.synchronize(); P["s_out"].synchronize()
+        self._have_hint = True
+        self.pipelined_calls = getattr(self, "pipelined_calls", 0) + 1
+        self.speculation_hits = getattr(self, "speculation_hits", 0) + (1 if ok else 0)
 
     def set_from_global(self, Q_global):
         self.set_local(np.asarray(Q_global)[self.lo_g:self.hi_g])

@@ -206,6 +206,15 @@ int hsd_aos_to_soa(const hsd_problem_t* p, const double* aos_dev, double* soa_de
 int hsd_soa_to_aos(const hsd_problem_t* p, const double* soa_dev, double* aos_dev, void* stream);
 /* CFL sweep: fills aux and lambda_max slot `slot` of scal (after zeroing it) */
 int hsd_wave_bounds(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot, void* stream);
+/* the same without zeroing the slot first: max(lambda) accumulates over several calls (sweeps of the windows of one grid)
+ *
+ * WINDOWS.  Every hsd_* call works on a sub-range of the cells of a grid when it is given a window descriptor: a copy of the
+ * grid's hsd_problem_t with ncells = cells of the window (nprob = 1, stride = row pitch of the full arrays unchanged) and array
+ * pointers advanced to the window's first cell.  With ghost_mask bits set for the ends that are not physical boundaries, hsd_step
+ * on the windows [b_i - 2, b_i+1) updates exactly the cells [b_i - 1, b_i+1 - 1): this is how hs_step_host and
+ * SlabSolver.step_host process a grid chunk by chunk while it is still arriving over the host link.  (Even window starts keep the
+ * single-phase step on its tensor-map tile copies.) */
+int hsd_wave_bounds_acc(const hsd_problem_t* p, const double* Q, double* aux, double* scal, int slot, void* stream);
 /* one fused step n: reads Qin/aux_in and slot n%3, writes Qout/aux_out and slot (n+1)%3;
  * if dt_hist != NULL the step's dt of problem p is stored at dt_hist[p*hist_cap + hist_k] (hist_k < 0: at the index the
  * per-problem counter inside `scal` holds, which the kernel then increments -- what lets a captured CUDA graph of steps be replayed).

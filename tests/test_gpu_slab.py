@@ -206,3 +206,89 @@ def test_exchange_gives_up_on_a_dead_peer(gpu):
     env = dict(os.environ, HS_EXCHANGE_TIMEOUT_S="1")
     out = subprocess.run([sys.executable, os.path.join(HERE, "exchange_timeout_check.py")], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "EXCHANGE-TIMEOUT-OK" in out.stdout, out.stdout[-1000:] + out.stderr[-3000:]
+
+
+def _step_host_worker(rank, world, port, nx, nsteps, q, exchange="p2p"):
+    """every rank keeps its slab (halo cells included) in pinned host memory and steps it with the chunk-pipelined
+    SlabSolver.step_host; the gathered result must equal the single-GPU resident run bit for bit"""
+    os.environ["HS_EXCHANGE"] = exchange
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import hyperelasticsolver_b200 as hs
+        from hyperelasticsolver_b200.slab import CudaKernels, SlabSolver
+        eos = hs.Barton2009()
+        Ql, Qr = hs.hyperelasticity.initial_states(eos, 1, device=rank)
+        x = (np.arange(nx) + 0.5) / nx
+        w = (0.5 * (1 + np.tanh((x - 0.5) / 0.02)))[:, None]
+        Q0 = np.ascontiguousarray((1 - w) * Ql[None, :] + w * Qr[None, :])
+        sol = SlabSolver(CudaKernels(eos, hs.SP13, f"cuda:{rank}"), nx)
+        a = torch.as_tensor(Q0[sol.lo_g:sol.hi_g].copy()).pin_memory()
+        b = torch.empty_like(a).pin_memory()
+        for _ in range(nsteps):
+            sol.step_host(a, b, hs.HLL, 0.6, 1.0 / nx, chunk=2048)
+            a, b = b, a
+        mine = a.numpy()[sol.a - sol.lo_g: sol.b - sol.lo_g]
+        parts = [None] * world
+        dist.all_gather_object(parts, (sol.a, sol.b, mine, sol.pipelined_calls, sol.speculation_hits))
+        if rank == 0:
+            Q = np.empty_like(Q0)
+            for (pa, pb, qq, _, _) in parts:
+                Q[pa:pb] = qq
+            with hs.Solver(eos, nx, model=hs.SP13, device=0) as s1:
+                s1.upload(Q0); s1.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=nsteps)
+                ref = s1.download()
+            q.put((bool(np.array_equal(ref, Q)), float(np.abs(ref - Q).max()), [(p[3], p[4]) for p in parts], sol.exchange))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_pipelined_step_host(gpu, exchange):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    nsteps = 6
+    procs = [ctx.Process(target=_step_host_worker, args=(r, 2, port, 40000, nsteps, q, exchange)) for r in range(2)]
+    for p in procs: p.start()
+    same, err, stats, kind = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120); assert p.exitcode == 0
+    assert same, err
+    assert stats == [(nsteps, nsteps - 1)] * 2, stats
+
+
+def test_slab_solver_pipelined_step_host_single_rank(gpu):
+    """world = 1: SlabSolver.step_host (pipelined, python host) == hs_step_host (pipelined, C) == the resident loop, bit for bit"""
+    import torch
+    hs = gpu
+    from hyperelasticsolver_b200.slab import CudaKernels, SlabSolver
+    nx, nsteps = 30000, 5
+    for model in ("sp13", "mph30"):
+        if model == "sp13":
+            eos = hs.Barton2009(); Ql, Qr = hs.hyperelasticity.initial_states(eos, 1); hm = hs.SP13
+        else:
+            eos = (hs.Barton2009(), hs.Barton2009()); Ql, Qr = hs.initial_states(eos, 6); hm = hs.MPH30
+        Q0 = hs.initial_condition(Ql, Qr, nx)
+        sol = SlabSolver(CudaKernels(eos, hm, "cuda:0"), nx)
+        a = torch.as_tensor(Q0.copy()).pin_memory(); b = torch.empty_like(a).pin_memory()
+        for _ in range(nsteps):
+            sol.step_host(a, b, hs.HLL, 0.6, 1.0 / nx, chunk=4096); a, b = b, a
+        assert (sol.pipelined_calls, sol.speculation_hits) == (nsteps, nsteps - 1)
+        with hs.Solver(eos, nx, model=hm) as s1:
+            s1.upload(Q0); s1.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=nsteps)
+            assert np.array_equal(s1.download(), a.numpy())
+        # and the serial form
+        sol2 = SlabSolver(CudaKernels(eos, hm, "cuda:0"), nx)
+        a2 = torch.as_tensor(Q0.copy()).pin_memory(); b2 = torch.empty_like(a2).pin_memory()
+        for _ in range(nsteps):
+            sol2.step_host_serial(a2, b2, hs.HLL, 0.6, 1.0 / nx); a2, b2 = b2, a2
+        assert np.array_equal(a2.numpy(), a.numpy())

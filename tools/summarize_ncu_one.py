@@ -47,6 +47,7 @@ if tkey:
     tp = 'profiles/step_kernel_traffic.json'
     tj = json.load(open(tp))
     tj[tkey] = {'dram_bytes_per_launch': traffic, 'fp64_pipe_pct_of_peak': round(fp64, 1), 'dram_pct_of_measured_copy_peak': round(dramp, 1),
-                'registers_per_thread': int(vals['launch__registers_per_thread'][0]), 'warps_per_sm': 16, 'source': out}
+                'registers_per_thread': int(vals['launch__registers_per_thread'][0]), 'warps_per_sm': 16, 'source': out,
+                'fp64_inst_per_cell_update': round(fp / (nthreads / 32) * per, 1), 'inst_per_cell_update': round(t2 / (nthreads / 32) * per, 1)}
     json.dump(tj, open(tp, 'w'), indent=1)
 print(traffic, fp64, dramp, dict(mix.most_common(14)))
