@@ -215,6 +215,38 @@ int launch_step_qp(int flux, int gen, const StepArgs& a, cudaStream_t st) {
   return gen ? HS_QP(FLUX_LXF, true) : HS_QP(FLUX_LXF, false);
 #undef HS_QP
 }
+// nsteps steps in one cooperative launch (k_step_qp_loop); HS_ERR_ARG-free "not possible" answer: returns 1 when the grid cannot be
+// co-resident or cooperative launches are unsupported, so that the caller falls back to one launch per step
+template <int FLUX, bool GEN, bool SAME>
+int launch_step_qp_loop_s(StepArgs a, int nsteps, cudaStream_t st, bool* done) {
+  constexpr size_t smem = qp_smem_doubles() * sizeof(double);
+  *done = false;
+  int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  CU(cudaGetDevice(&dev));
+  static std::atomic<unsigned> attr_dev_mask{0};
+  if (!(attr_dev_mask.load() & (1u << (dev & 31)))) {
+    CU(cudaFuncSetAttribute(k_step_qp_loop<FLUX, GEN, SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev_mask.fetch_or(1u << (dev & 31));
+  }
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_qp_loop<FLUX, GEN, SAME>, QP_T, smem));
+  a.tiles_per_prob = (a.ncells - 2 + (QP_CPB - 2) - 1) / (QP_CPB - 2);
+  const long long nb = (long long)a.tiles_per_prob * a.nprob;
+  if (!coop || nb > (long long)per_sm * sms) return HS_OK;
+  void* args[] = {&a, &nsteps};
+  CU(cudaLaunchCooperativeKernel((void*)k_step_qp_loop<FLUX, GEN, SAME>, dim3((unsigned)nb), dim3(QP_T), args, smem, st));
+  g_launches++;
+  *done = true;
+  return HS_OK;
+}
+int launch_step_qp_loop(int flux, int gen, const StepArgs& a, int nsteps, cudaStream_t st, bool* done) {
+  const bool same = std::memcmp(&a.eos.e[0], &a.eos.e[1], sizeof(EosDev)) == 0;
+#define HS_QPL(F, G)  (same ? launch_step_qp_loop_s<F, G, true>(a, nsteps, st, done) : launch_step_qp_loop_s<F, G, false>(a, nsteps, st, done))
+  if (flux == HS_FLUX_HLL) return gen ? HS_QPL(FLUX_HLL, true) : HS_QPL(FLUX_HLL, false);
+  return gen ? HS_QPL(FLUX_LXF, true) : HS_QPL(FLUX_LXF, false);
+#undef HS_QPL
+}
 // two-phase grids up to this many cells (all problems together) take k_step_qp; HS_QP_MAX_CELLS=0 disables it
 int64_t qp_max_cells() {
   const char* e = std::getenv("HS_QP_MAX_CELLS");
@@ -330,12 +362,11 @@ int hsd_wave_bounds_acc(const hsd_problem_t* p, const double* Q, double* aux, do
   return wave_bounds_impl(p, Q, aux, scal, slot, nullptr, (cudaStream_t)stream, true);
 }
 
-int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
-             const double* aux_in, double* Qout, double* aux_out, double* scal,
-             double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, void* stream) {
+static int make_step_args(StepArgs& a, const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
+                          const double* aux_in, double* Qout, double* aux_out, double* scal,
+                          double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask) {
   if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
   if (ghost_mask < 0 || ghost_mask > 3) return fail(HS_ERR_ARG, "ghost_mask must be 0..3");
-  StepArgs a;
   a.Qin = Qin; a.Qout = Qout; a.aux_in = aux_in; a.aux_out = aux_out;
   a.lam = scal_lam(scal); a.tt = scal_t(scal, p->nprob); a.steps = scal_steps(scal, p->nprob);
   a.status = scal_status(scal, p->nprob);
@@ -348,6 +379,16 @@ int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_e
   static const unsigned long long spin_ns = 1000000000ull * (unsigned long long)(std::getenv("HS_TMA_TIMEOUT_S") ? std::atoi(std::getenv("HS_TMA_TIMEOUT_S")) : 10);
   a.spin_ns = spin_ns;
   a.eos = eos_pair(p);
+  a.tiles_per_prob = 0;
+  return HS_OK;
+}
+
+int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
+             const double* aux_in, double* Qout, double* aux_out, double* scal,
+             double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, void* stream) {
+  StepArgs a;
+  const int rca = make_step_args(a, p, flux, cfl, dx, t_end, n, Qin, aux_in, Qout, aux_out, scal, dt_hist, hist_k, hist_cap, ghost_mask);
+  if (rca) return rca;
   if (p->model == HS_MODEL_MPH30) {
     if (p->ncells * p->nprob <= qp_max_cells()) return launch_step_qp(flux, p->gen, a, (cudaStream_t)stream);
     constexpr int T = T_STEP_MPH, CPB = T / 2;
@@ -775,6 +816,8 @@ int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64
   // needs a handful of synchronisations; kernels launched past t_end are no-ops (same overshoot semantics as main.jl:202,214).
   const char* eg = std::getenv("HS_GRAPH");
   const bool use_graph = c->parts.size() == 1 && !(eg && eg[0] == '0');
+  const char* el = std::getenv("HS_QP_LOOP");
+  const bool use_loop = c->parts.size() == 1 && c->model == HS_MODEL_MPH30 && c->ncells * c->nprob <= qp_max_cells() && !(el && el[0] == '0');
   std::vector<double> tv;
   int64_t done = 0;
   while (done < max_steps) {
@@ -800,7 +843,20 @@ int hs_advance(hs_ctx_t* c, int flux, double cfl, double dx, double t_end, int64
     }
     if (m > max_steps - done) m = max_steps - done;
     int64_t k = 0;
-    if (use_graph && m >= 12) {
+    if (use_loop && m >= 2) {   // small two-phase grid: the whole stretch in one cooperative launch (grid barrier between the steps)
+      Part& p = c->parts[0];
+      PART_ENTER(p);
+      const int a = (int)(c->n & 1), b = a ^ 1;
+      StepArgs sa;
+      int rc = make_step_args(sa, &p.prob, flux, cfl, dx, t_end, c->n, p.Q[a], p.aux[a], p.Q[b], p.aux[b], p.scal, hist_cap > 0 ? p.dt_hist : nullptr,
+                              -1, hist_cap, p.ghost);
+      if (rc) return rc;
+      bool launched = false;
+      rc = launch_step_qp_loop(flux, p.prob.gen, sa, (int)m, p.stream, &launched);
+      if (rc) return rc;
+      if (launched) { c->n += m; k = m; }
+    }
+    if (use_graph && m - k >= 12) {
       for (; k + 6 <= m; k += 6) { int rc = launch_six_steps(c, flux, cfl, dx, t_end, hist_cap); if (rc) return rc; }
     }
     for (; k < m; ++k) { int rc = enqueue_step(c, flux, cfl, dx, t_end, -1, hist_cap); if (rc) return rc; }

@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 #include "hs_phase.cuh"
@@ -649,10 +650,14 @@ __device__ __forceinline__ int qp_node(const EosDev& eos, const double* b14, con
   return st.bad;
 }
 
-template <int FLUX, bool GEN, bool SAME>
-__global__ void __launch_bounds__(QP_T, 1) k_step_qp(const StepArgs g) {
+// One step of k_step_qp on the buffers / scalar slots given (the persistent variant k_step_qp_loop rotates them itself).
+// COHERENT: the inputs were written by other blocks of the SAME launch (previous step of the persistent loop): loads must
+// come from L2 (ld.global.cg), not through the non-coherent path.
+template <int FLUX, bool GEN, bool SAME, bool COHERENT>
+__device__ __forceinline__ void qp_step_body(const StepArgs& g, const double* Qin, double* Qout, const double* aux_in, double* aux_out,
+                                             int cur, int nxt, int clr, double* smem) {
   constexpr int T = QP_NP, CPB = QP_CPB;   // (T: row stride of the shared tiles, as the HS_FLUX macro expects)
-  extern __shared__ double smem[];
+  auto ld = [](const double* ptr) { return COHERENT ? __ldcg(ptr) : __ldg(ptr); };
   double* Rs = smem;                 // records              [15][32]
   double* Fs = Rs + 15 * T;          // physical flux        [11][32]  (flux_row)
   double* H1 = Fs + 11 * T;          // Q_hll - Q_l          [15][32]
@@ -676,17 +681,16 @@ __global__ void __launch_bounds__(QP_T, 1) k_step_qp(const StepArgs g) {
   const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
   const EosDev& eos = g.eos.e[SAME ? 0 : ph];
 
-  for (int j = warp; j < 15; j += QP_WARPS) Rs[j * T + lane] = __ldg(g.Qin + (size_t)(15 * ph + j) * g.stride + gi);
-  if (warp == QP_WARPS - 1 && ph == 0) { lo_s[l] = __ldg(g.aux_in + gi); hi_s[l] = __ldg(g.aux_in + g.stride + gi); }
+  for (int j = warp; j < 15; j += QP_WARPS) Rs[j * T + lane] = ld(Qin + (size_t)(15 * ph + j) * g.stride + gi);
+  if (warp == QP_WARPS - 1 && ph == 0) { lo_s[l] = ld(aux_in + gi); hi_s[l] = ld(aux_in + g.stride + gi); }
   if (tid == 0) {
-    const unsigned long long lam_bits = __ldg(g.lam + (size_t)g.cur * g.nprob + prob);
-    const double lam_cur = __longlong_as_double((long long)lam_bits);
+    const double lam_cur = ld(reinterpret_cast<const double*>(g.lam) + (size_t)cur * g.nprob + prob);
     const double dt0 = g.cfl * g.dx / lam_cur;           // main.jl:212
     const double lambda0 = g.dx / dt0;                   // main.jl:223
     sc[0] = dt0;
     sc[1] = (FLUX == FLUX_HLL) ? dt0 / g.dx : 1.0 / lambda0;   // main.jl:225,59 / :40
     sc[2] = lambda0;
-    sc[3] = __ldg(g.tt + (size_t)g.cur * g.nprob + prob);
+    sc[3] = ld(g.tt + (size_t)cur * g.nprob + prob);
     sc[4] = lam_cur;
   }
   __syncthreads();
@@ -696,13 +700,13 @@ __global__ void __launch_bounds__(QP_T, 1) k_step_qp(const StepArgs g) {
   const bool own_frozen = valid && ((c == 0 && !(g.ghost & 1)) || (c == g.ncells - 1 && !(g.ghost & 2)));
   if (!active) {  // this problem already reached t_end: carry the state through unchanged
     if (own_interior || own_frozen) {
-      for (int j = warp; j < 15; j += QP_WARPS) g.Qout[(size_t)(15 * ph + j) * g.stride + gi] = Rs[j * T + lane];
-      if (warp == QP_WARPS - 1 && ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
+      for (int j = warp; j < 15; j += QP_WARPS) Qout[(size_t)(15 * ph + j) * g.stride + gi] = Rs[j * T + lane];
+      if (warp == QP_WARPS - 1 && ph == 0) { aux_out[gi] = lo_s[l]; aux_out[g.stride + gi] = hi_s[l]; }
     }
     if (tile == 0 && tid == 0) {
-      g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur;
-      g.lam[(size_t)g.nxt * g.nprob + prob] = (unsigned long long)__double_as_longlong(sc[4]);
-      g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
+      g.tt[(size_t)nxt * g.nprob + prob] = t_cur;
+      g.lam[(size_t)nxt * g.nprob + prob] = (unsigned long long)__double_as_longlong(sc[4]);
+      g.lam[(size_t)clr * g.nprob + prob] = 0ull;
     }
     return;
   }
@@ -811,7 +815,7 @@ __global__ void __launch_bounds__(QP_T, 1) k_step_qp(const StepArgs g) {
       const double q = Rs[j * T + lane];
       const double qn = own_interior ? cell_update(q, upd, Hm[j * T + tr], CR[j * T + lane]) : q;
       Rn[j * T + lane] = qn;
-      if (own_interior || own_frozen) g.Qout[(size_t)(15 * ph + j) * g.stride + gi] = qn;
+      if (own_interior || own_frozen) Qout[(size_t)(15 * ph + j) * g.stride + gi] = qn;
     }
   }
   __syncthreads();
@@ -830,25 +834,50 @@ __global__ void __launch_bounds__(QP_T, 1) k_step_qp(const StepArgs g) {
     double lamv = 0.0;
     if (own_interior) {
       bad |= sn.bad;
-      if (ph == 0) { g.aux_out[gi] = lo_n; g.aux_out[g.stride + gi] = hi_n; }
+      if (ph == 0) { aux_out[gi] = lo_n; aux_out[g.stride + gi] = hi_n; }
       lamv = fmax(fabs(lo_n), fabs(hi_n));
     } else if (own_frozen) {
-      if (ph == 0) { g.aux_out[gi] = lo_s[l]; g.aux_out[g.stride + gi] = hi_s[l]; }
+      if (ph == 0) { aux_out[gi] = lo_s[l]; aux_out[g.stride + gi] = hi_s[l]; }
       lamv = fmax(fabs(lo_s[l]), fabs(hi_s[l]));
     }
     lamv = warp_max_nonneg(lamv);
     if (lane == 0) {
-      atomicMax(g.lam + (size_t)g.nxt * g.nprob + prob, (unsigned long long)__double_as_longlong(lamv));
+      atomicMax(g.lam + (size_t)nxt * g.nprob + prob, (unsigned long long)__double_as_longlong(lamv));
       if (tile == 0) {
-        g.tt[(size_t)g.nxt * g.nprob + prob] = t_cur + dt;   // main.jl:214
+        g.tt[(size_t)nxt * g.nprob + prob] = t_cur + dt;   // main.jl:214
         g.steps[prob] += 1;                                   // main.jl:215
         hist_record(g, prob, dt);
-        g.lam[(size_t)g.clr * g.nprob + prob] = 0ull;
+        g.lam[(size_t)clr * g.nprob + prob] = 0ull;
       }
     }
   }
   bad = __any_sync(FULL, bad);
   if (bad && lane == 0) atomicOr(g.status, 1);
+}
+
+template <int FLUX, bool GEN, bool SAME>
+__global__ void __launch_bounds__(QP_T, 1) k_step_qp(const StepArgs g) {
+  extern __shared__ double smem[];
+  qp_step_body<FLUX, GEN, SAME, false>(g, g.Qin, g.Qout, g.aux_in, g.aux_out, g.cur, g.nxt, g.clr, smem);
+}
+
+// The device-resident loop of a small grid in ONE launch: nsteps steps of k_step_qp separated by grid-wide barriers
+// (cooperative launch: every block is resident), buffers and scalar slots rotated inside the kernel.  A step costs its own
+// latency (~3 us for nx = 1000) plus a barrier instead of a kernel launch (~5 us between dependent launches, graph or not).
+// Steps past t_end are no-ops, exactly as the host-launched sequence (the host sizes nsteps from the clock).
+template <int FLUX, bool GEN, bool SAME>
+__global__ void __launch_bounds__(QP_T, 1) k_step_qp_loop(const StepArgs g, const int nsteps) {
+  extern __shared__ double smem[];
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  double* const Qa = const_cast<double*>(g.Qin);
+  double* const Aa = const_cast<double*>(g.aux_in);
+  int cur = g.cur, nxt = g.nxt, clr = g.clr;
+  for (int s = 0; s < nsteps; ++s) {
+    const bool odd = s & 1;
+    qp_step_body<FLUX, GEN, SAME, true>(g, odd ? g.Qout : Qa, odd ? Qa : g.Qout, odd ? g.aux_out : Aa, odd ? Aa : g.aux_out, cur, nxt, clr, smem);
+    const int c0 = cur; cur = nxt; nxt = clr; clr = c0;
+    grid.sync();      // all writes of step s (state, cache rows, max(lambda), clock) visible to every block; shared tiles free again
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -63,10 +63,11 @@ def test_quadrature_parallel_kernel_bit_identical_to_fused_kernel(gpu, kind, flu
     Q0 = _smooth_two_phase(hs, eos, nx, 7 if kind == "hetero" else 6)
     nsteps = 9
     Qa, ha, ta, sa = _run(hs, eos, Q0, nsteps, flux, HS_QP_MAX_CELLS=0, HS_GRAPH=0)          # fused kernel k_step
-    Qb, hb, tb, sb = _run(hs, eos, Q0, nsteps, flux, HS_QP_MAX_CELLS=1 << 20, HS_GRAPH=0)    # k_step_qp
-    assert np.array_equal(ha, hb), (ha, hb)
-    assert np.array_equal(Qa, Qb), np.abs(Qa - Qb).max()
-    assert np.array_equal(ta, tb) and np.array_equal(sa, sb)
+    for loop in (0, 1):   # k_step_qp launched per step / k_step_qp_loop: all steps in one cooperative launch with grid barriers
+        Qb, hb, tb, sb = _run(hs, eos, Q0, nsteps, flux, HS_QP_MAX_CELLS=1 << 20, HS_GRAPH=0, HS_QP_LOOP=loop)
+        assert np.array_equal(ha, hb), (loop, ha, hb)
+        assert np.array_equal(Qa, Qb), (loop, np.abs(Qa - Qb).max())
+        assert np.array_equal(ta, tb) and np.array_equal(sa, sb)
 
 
 def test_quadrature_parallel_kernel_ensemble_and_slabs(gpu):
@@ -82,15 +83,16 @@ def test_quadrature_parallel_kernel_ensemble_and_slabs(gpu):
     Qlr = hs.prim2cons_mph(eos, P)
     Q0 = np.where((np.arange(nx) < nx / 2)[None, :, None], Qlr[:, None, 0, :], Qlr[:, None, 1, :]).copy()
     outs = []
-    for cap in (0, 1 << 20):
-        with env(HS_QP_MAX_CELLS=cap), hs.Solver(eos, nx, nprob=nprob) as sol:
+    for cap, loop in ((0, 0), (1 << 20, 0), (1 << 20, 1)):
+        with env(HS_QP_MAX_CELLS=cap, HS_QP_LOOP=loop), hs.Solver(eos, nx, nprob=nprob) as sol:
             sol.upload(Q0)
             lam = sol.wave_speeds()
             t_end = 7.3 * 0.6 * (1.0 / nx) / lam.max()
             hist = sol.advance(t_end, "hll", 0.6, 1.0 / nx, max_steps=60, record_dt=True)
             outs.append((sol.download(), hist, sol.t.copy(), sol.steps.copy()))
-    for x, y in zip(outs[0], outs[1]):
-        assert np.array_equal(x, y)
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert np.array_equal(x, y)
     assert len(set(outs[0][3].tolist())) > 1          # the problems really stop at different step counts
     # slab windows with ghost cells through hsd_step (every slab small enough for k_step_qp), against the fused kernel on the whole grid
     nx = 1500
@@ -110,8 +112,8 @@ def test_graph_replay_bit_identical_and_termination(gpu, model, nx):
     else:
         eos = hs.Barton2009(); Ql, Qr = hs.hyperelasticity.initial_states(eos, 1); Q0 = hs.initial_condition(Ql, Qr, nx); hm = hs.SP13
     res = []
-    for graph in (0, 1):
-        with env(HS_GRAPH=graph), hs.Solver(eos, nx, model=hm) as sol:
+    for graph, loop in ((0, 0), (1, 0), (1, 1)):
+        with env(HS_GRAPH=graph, HS_QP_LOOP=loop), hs.Solver(eos, nx, model=hm) as sol:
             sol.upload(Q0)
             lam = sol.wave_speeds()[0]
             t_end = 100.4 * 0.6 * (1.0 / nx) / lam            # ~100-140 steps; the clock decides, not max_steps
@@ -124,7 +126,8 @@ def test_graph_replay_bit_identical_and_termination(gpu, model, nx):
             # a second stretch from a non-zero clock and an odd position in the buffer rotation
             sol.advance(2 * t_end, "hll", 0.6, 1.0 / nx, max_steps=37)
             res.append((sol.download(), hist.copy(), float(sol.t[0]), int(sol.steps[0])))
-    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][2:] == res[1][2:]
+    for r in res[1:]:
+        assert np.array_equal(res[0][0], r[0]) and np.array_equal(res[0][1], r[1]) and res[0][2:] == r[2:]
 
 
 def test_config0_through_graph_and_small_grid_kernel(gpu, oracle):
