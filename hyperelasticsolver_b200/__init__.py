@@ -8,7 +8,7 @@ libhyperelastic_b200.so on the GPU.  There is no CPU fallback.
 from ._lib import (Barton2009, Hank2016, DomainError, HyperelasticError, HLL, LXF, MPH30, SP13, build, lib)
 from .hyperelasticity_mph import (cons2prim_mph, flux_mph, get_eigvals, initial_states, noncons_flux, prim2cons_mph)
 from .num_fluxes import hll, lxf
-from .solver import Solver, initial_condition, update_cell, register_host, unregister_host
+from .solver import Solver, Solver2D, initial_condition, update_cell, register_host, unregister_host
 from . import hyperelasticity
 from . import equations_of_state
 

@@ -82,6 +82,12 @@ SIGNATURES = {
     "hs_host_register": (C.c_int, [_vp, C.c_size_t]),
     "hs_host_unregister": (C.c_int, [_vp]),
     "hs_step_host_stats": (C.c_int, [_vp, _ip, _ip]),
+    "hs2d_create": (C.c_int, [C.POINTER(_vp), C.c_int, _eosp, C.c_int, _i64, _i64, C.c_int]),
+    "hs2d_destroy": (C.c_int, [_vp]),
+    "hs2d_upload": (C.c_int, [_vp, _vp]),
+    "hs2d_download": (C.c_int, [_vp, _vp]),
+    "hs2d_step": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, _vp]),
+    "hs2d_advance": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _vp, _vp]),
     "hs_cons2prim": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),
     "hs_prim2cons": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),
     "hs_flux": (C.c_int, [C.c_int, _eosp, C.c_int, _vp, _vp, _i64, C.c_int]),

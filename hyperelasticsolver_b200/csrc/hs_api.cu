@@ -164,7 +164,8 @@ int launch_step_sp(const StepArgs& a, int64_t ntiles, int kper, cudaStream_t st)
   const char* e2 = std::getenv("HS_SP_TMA2D");
   CUtensorMap mq, ma;
   std::memset(&mq, 0, sizeof mq); std::memset(&ma, 0, sizeof ma);
-  const bool tm2d = !(e2 && e2[0] == '0') && (a.stride % 2 == 0) && a.stride < 0x7fffffffLL &&
+  // (every tile must start on a 16-byte boundary: even row pitch, and even problem length when there are several problems)
+  const bool tm2d = !(e2 && e2[0] == '0') && (a.stride % 2 == 0) && (a.nprob == 1 || a.ncells % 2 == 0) && a.stride < 0x7fffffffLL &&
                     make_tile_map(&mq, a.Qin, (long long)a.ncells * a.nprob, a.stride, 13) &&
                     make_tile_map(&ma, a.aux_in, (long long)a.ncells * a.nprob, a.stride, SP_NAX);
   if (tm2d) {
@@ -380,15 +381,28 @@ static int make_step_args(StepArgs& a, const hsd_problem_t* p, int flux, double 
   a.spin_ns = spin_ns;
   a.eos = eos_pair(p);
   a.tiles_per_prob = 0;
+  a.dt_shared = nullptr;
   return HS_OK;
 }
+
+static int step_impl(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
+                     const double* aux_in, double* Qout, double* aux_out, double* scal,
+                     double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, const double* dt_shared, void* stream);
 
 int hsd_step(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
              const double* aux_in, double* Qout, double* aux_out, double* scal,
              double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, void* stream) {
+  return step_impl(p, flux, cfl, dx, t_end, n, Qin, aux_in, Qout, aux_out, scal, dt_hist, hist_k, hist_cap, ghost_mask, nullptr, stream);
+}
+
+// dt_shared (device scalar, may be null): every problem of the launch steps with this dt -- the sweeps of the dimension-split 2-D solver
+static int step_impl(const hsd_problem_t* p, int flux, double cfl, double dx, double t_end, int64_t n, const double* Qin,
+                     const double* aux_in, double* Qout, double* aux_out, double* scal,
+                     double* dt_hist, int64_t hist_k, int64_t hist_cap, int ghost_mask, const double* dt_shared, void* stream) {
   StepArgs a;
   const int rca = make_step_args(a, p, flux, cfl, dx, t_end, n, Qin, aux_in, Qout, aux_out, scal, dt_hist, hist_k, hist_cap, ghost_mask);
   if (rca) return rca;
+  a.dt_shared = dt_shared;
   if (p->model == HS_MODEL_MPH30) {
     if (p->ncells * p->nprob <= qp_max_cells()) return launch_step_qp(flux, p->gen, a, (cudaStream_t)stream);
     constexpr int T = T_STEP_MPH, CPB = T / 2;
@@ -1090,6 +1104,193 @@ int hs_step_host_stats(hs_ctx_t* c, int64_t* pipelined_calls, int64_t* speculati
   if (pipelined_calls) *pipelined_calls = c->pipelined_calls;
   if (speculation_hits) *speculation_hits = c->speculation_hits;
   return HS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dimension-split 2-D solver: Godunov splitting Q^{n+1} = Y(dt) X(dt) Q^n on an nx x ny grid.  X = the 1-D
+// step on every grid row (an ensemble of ny rows of nx cells with ONE dt), Y = the same kernels on the columns of the grid seen
+// from the frame rotated by R e_2 = e_1 (k_transpose_rot).  dt = cfl min(dx / max lambda_x, dy / max lambda_y); every sweep is the
+// reference's 1-D step on each grid line INCLUDING its boundary rule (first and last cell of the line frozen, main.jl:219-220): the
+// x-sweep freezes the first / last column, the y-sweep the first / last row, so only the four corner cells never change.  The reference driver is 1-D; this is the "natural growth of
+// the same kernels" the physics' normal argument (EquationsOfState.jl:223, HyperelasticityMPh.jl:264) points to, validated by
+// what can be validated exactly: a grid uniform in y reproduces the 1-D solver bit for bit in every row, a grid uniform in x
+// with states rotated by R^T reproduces it in every column, and the first dt equals the one from get_eigvals with normals e_1, e_2.
+// ---------------------------------------------------------------------------------------------
+struct hs2d_ctx {
+  int model = 0, nvar = 0, nphase = 0, device = 0;
+  int64_t nx = 0, ny = 0;
+  hsd_problem_t px, py;          // ensembles: ny rows of nx cells / nx columns of ny cells
+  cudaStream_t stream = nullptr;
+  double* Qx[2] = {nullptr, nullptr};  double* Qy[2] = {nullptr, nullptr};
+  double* ax[2] = {nullptr, nullptr};  double* ay[2] = {nullptr, nullptr};
+  double* sx = nullptr; double* sy = nullptr;   // scalar blocks of the two ensembles
+  double* clock = nullptr;       // [t, dt, steps, lambda_x, lambda_y]
+  double* stage = nullptr;
+  int64_t n = 0;                 // steps taken since upload (selects the scalar slots of both ensembles)
+  RotMap fwd, back;
+};
+
+static RotMap make_rotmap(int model, bool forward) {
+  RotMap m;
+  std::memset(&m, 0, sizeof m);
+  m.nvar = model == HS_MODEL_MPH30 ? 30 : 13;
+  for (int v = 0; v < 30; ++v) { m.src[v] = v; m.sign[v] = 1.0; }
+  // forward (state in the frame rotated by R = [[0,1,0],[-1,0,0],[0,0,1]]): component 1' = component 2, component 2' = -component 1
+  // back (R^T): component 1 = -component 2', component 2 = component 1'
+  auto pair = [&](int i1, int i2) {   // variables holding the first / second spatial component of a vector (u, or a column of F)
+    if (forward) { m.src[i1] = i2; m.sign[i1] = 1.0; m.src[i2] = i1; m.sign[i2] = -1.0; }
+    else { m.src[i1] = i2; m.sign[i1] = -1.0; m.src[i2] = i1; m.sign[i2] = 1.0; }
+  };
+  if (model == HS_MODEL_MPH30) {
+    for (int p = 0; p < 2; ++p) {
+      pair(15 * p + 2, 15 * p + 3);                                         // momentum
+      for (int j = 0; j < 3; ++j) pair(15 * p + 6 + 3 * j, 15 * p + 7 + 3 * j);   // A column-major: rows 1, 2 of column j
+    }
+  } else {
+    pair(0, 1);                                                             // momentum
+    for (int j = 0; j < 3; ++j) pair(3 + j, 6 + j);                         // rho F row-major: rows 1, 2, column j
+  }
+  return m;
+}
+
+static int transpose_rot(hs2d_ctx* c, const double* in, double* out, int64_t rows, int64_t cols, const RotMap& map) {
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)c->nvar), block(32, 8);
+  k_transpose_rot<<<grid, block, 0, c->stream>>>(in, out, (int)rows, (int)cols, map);
+  g_launches++;
+  CU(cudaGetLastError());
+  return HS_OK;
+}
+
+int hs2d_destroy(hs2d_ctx_t* c) {
+  if (!c) return HS_OK;
+  DeviceGuard g(c->device);
+  for (int k = 0; k < 2; ++k) { cudaFree(c->Qx[k]); cudaFree(c->Qy[k]); cudaFree(c->ax[k]); cudaFree(c->ay[k]); }
+  cudaFree(c->sx); cudaFree(c->sy); cudaFree(c->clock); cudaFree(c->stage);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return HS_OK;
+}
+
+int hs2d_create(hs2d_ctx_t** out, int model, const hs_barton2009_t* eos, int nphase, int64_t nx, int64_t ny, int device) {
+  if (!out) return fail(HS_ERR_ARG, "null ctx pointer");
+  *out = nullptr;
+  if (hs_device_count() <= 0) return fail(HS_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  if (nx < 3 || ny < 3) return fail(HS_ERR_ARG, "need nx >= 3 and ny >= 3");
+  if (nx * ny > 0x7fffffffLL) return fail(HS_ERR_ARG, "nx * ny exceeds 2^31-1");
+  hs2d_ctx* c = new hs2d_ctx();
+  int rc = hsd_problem_init(&c->px, model, eos, nphase, nx, ny);
+  if (!rc) rc = hsd_problem_init(&c->py, model, eos, nphase, ny, nx);
+  if (rc) { delete c; return rc; }
+  c->model = model; c->nvar = model == HS_MODEL_MPH30 ? 30 : 13; c->nphase = nphase; c->nx = nx; c->ny = ny; c->device = device;
+  c->fwd = make_rotmap(model, true); c->back = make_rotmap(model, false);
+  DeviceGuard g(device);
+  if (!g.ok) { delete c; return fail(HS_ERR_CUDA, "cudaSetDevice failed"); }
+  const size_t nq = (size_t)c->nvar * nx * ny * sizeof(double), na = (size_t)HS_NAUX(model) * nx * ny * sizeof(double);
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    e = cudaMalloc(&c->Qx[k], nq);
+    if (e == cudaSuccess) e = cudaMalloc(&c->Qy[k], nq);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ax[k], na);
+    if (e == cudaSuccess) e = cudaMalloc(&c->ay[k], na);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&c->sx, sizeof(double) * HS_SCAL_DOUBLES(ny));
+  if (e == cudaSuccess) e = cudaMalloc(&c->sy, sizeof(double) * HS_SCAL_DOUBLES(nx));
+  if (e == cudaSuccess) e = cudaMalloc(&c->clock, sizeof(double) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&c->stage, nq);
+  if (e != cudaSuccess) { g_err = std::string("device allocation failed: ") + cudaGetErrorString(e); hs2d_destroy(c); return HS_ERR_CUDA; }
+  *out = c;
+  return HS_OK;
+}
+
+static int hs2d_status(hs2d_ctx* c) {
+  int stx = 0, sty = 0;
+  CU(cudaMemcpyAsync(&stx, scal_status(c->sx, c->ny), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&sty, scal_status(c->sy, c->nx), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if ((stx | sty) & 4) return fail(HS_ERR_CUDA, "tile copy (TMA) did not complete: internal error of the single-phase step kernel");
+  if (stx | sty) return fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError");
+  return HS_OK;
+}
+
+/* Q: (nvar, nx, ny) column-major = Julia Array{Float64,3}(nvar, nx, ny): cell (i, j) is record i + nx j */
+int hs2d_upload(hs2d_ctx_t* c, const double* Q) {
+  if (!c || !Q) return fail(HS_ERR_ARG, "null argument");
+  DeviceGuard g(c->device);
+  const size_t nq = (size_t)c->nvar * c->nx * c->ny * sizeof(double);
+  CU(cudaMemcpyAsync(c->stage, Q, nq, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(c->sx, 0, sizeof(double) * HS_SCAL_DOUBLES(c->ny), c->stream));
+  CU(cudaMemsetAsync(c->sy, 0, sizeof(double) * HS_SCAL_DOUBLES(c->nx), c->stream));
+  CU(cudaMemsetAsync(c->clock, 0, sizeof(double) * 8, c->stream));
+  c->n = 0;
+  int rc = hsd_aos_to_soa(&c->px, c->stage, c->Qx[0], c->stream); if (rc) return rc;
+  rc = hsd_wave_bounds(&c->px, c->Qx[0], c->ax[0], c->sx, 0, c->stream); if (rc) return rc;               // lambda_x per row, cache rows
+  rc = transpose_rot(c, c->Qx[0], c->Qy[0], c->ny, c->nx, c->fwd); if (rc) return rc;
+  rc = hsd_wave_bounds(&c->py, c->Qy[0], c->ay[0], c->sy, 0, c->stream); if (rc) return rc;               // lambda_y per column
+  return hs2d_status(c);
+}
+
+int hs2d_download(hs2d_ctx_t* c, double* Q) {
+  if (!c || !Q) return fail(HS_ERR_ARG, "null argument");
+  DeviceGuard g(c->device);
+  int rc = hsd_soa_to_aos(&c->px, c->Qx[0], c->stage, c->stream); if (rc) return rc;
+  CU(cudaMemcpyAsync(Q, c->stage, (size_t)c->nvar * c->nx * c->ny * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return HS_OK;
+}
+
+static int hs2d_enqueue_step(hs2d_ctx* c, int flux, double cfl, double dx, double dy, double t_end) {
+  const int64_t n = c->n;
+  const int cur = (int)(n % 3), nxt = (int)((n + 1) % 3);
+  k_dt2d<<<1, 256, 0, c->stream>>>(scal_lam(c->sx) + (size_t)cur * c->ny, (int)c->ny, scal_lam(c->sy) + (size_t)cur * c->nx, (int)c->nx,
+                                  cfl, dx, dy, t_end, c->clock);
+  g_launches++;
+  CU(cudaGetLastError());
+  const double* dt = c->clock + 1;
+  // X(dt): rows
+  int rc = step_impl(&c->px, flux, cfl, dx, t_end, n, c->Qx[0], c->ax[0], c->Qx[1], c->ax[1], c->sx, nullptr, 0, 0, 0, dt, c->stream); if (rc) return rc;
+  // columns of the intermediate state in the rotated frame, their cache rows
+  rc = transpose_rot(c, c->Qx[1], c->Qy[0], c->ny, c->nx, c->fwd); if (rc) return rc;
+  rc = hsd_wave_bounds(&c->py, c->Qy[0], c->ay[0], c->sy, cur, c->stream); if (rc) return rc;
+  // Y(dt): columns; the tail of the step leaves lambda_y of the NEW state in slot nxt
+  rc = step_impl(&c->py, flux, cfl, dy, t_end, n, c->Qy[0], c->ay[0], c->Qy[1], c->ay[1], c->sy, nullptr, 0, 0, 0, dt, c->stream); if (rc) return rc;
+  // back to rows; cache rows and lambda_x of the new state (slot nxt of the row ensemble)
+  rc = transpose_rot(c, c->Qy[1], c->Qx[0], c->nx, c->ny, c->back); if (rc) return rc;
+  rc = hsd_wave_bounds(&c->px, c->Qx[0], c->ax[0], c->sx, nxt, c->stream); if (rc) return rc;
+  c->n += 1;
+  return HS_OK;
+}
+
+int hs2d_step(hs2d_ctx_t* c, int flux, double cfl, double dx, double dy, double* dt_out) {
+  if (!c) return fail(HS_ERR_ARG, "null context");
+  if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
+  DeviceGuard g(c->device);
+  int rc = hs2d_enqueue_step(c, flux, cfl, dx, dy, 1.0e300); if (rc) return rc;
+  if (dt_out) CU(cudaMemcpyAsync(dt_out, c->clock + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return hs2d_status(c);
+}
+
+int hs2d_advance(hs2d_ctx_t* c, int flux, double cfl, double dx, double dy, double t_end, int64_t max_steps, double* t_out, int64_t* steps_out) {
+  if (!c) return fail(HS_ERR_ARG, "null context");
+  if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
+  if (max_steps < 0) return fail(HS_ERR_ARG, "max_steps < 0");
+  DeviceGuard g(c->device);
+  double clk[3] = {0, 0, 0};
+  int64_t done = 0;
+  while (done < max_steps) {
+    CU(cudaMemcpyAsync(clk, c->clock, sizeof clk, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!(clk[0] < t_end)) break;
+    int64_t m = 16;
+    if (clk[1] > 0.0) { m = (int64_t)((t_end - clk[0]) / clk[1]) - 2; if (m > 4096) m = 4096; if (m < 1) m = 1; }
+    if (m > max_steps - done) m = max_steps - done;
+    for (int64_t k = 0; k < m; ++k) { int rc = hs2d_enqueue_step(c, flux, cfl, dx, dy, t_end); if (rc) return rc; }
+    done += m;
+  }
+  CU(cudaMemcpyAsync(clk, c->clock, sizeof clk, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (t_out) *t_out = clk[0];
+  if (steps_out) *steps_out = (int64_t)clk[2];
+  return hs2d_status(c);
 }
 
 // ---------------------------------------------------------------------------------------------

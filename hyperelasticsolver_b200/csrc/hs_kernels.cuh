@@ -371,6 +371,7 @@ struct StepArgs {
   int ghost;                 // bit 0 / 1: the first / last cell is a halo copy owned by a neighbouring slab
   double cfl, dx, t_end;
   unsigned long long spin_ns;   // time limit of the tile-copy wait of k_step_sp (never hang the GPU on a lost copy)
+  const double* dt_shared;      // not null: every problem steps with this dt (device scalar) instead of cfl dx / its own max(lambda)
   EosPair eos;
 };
 
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(T, (MODEL == MODEL_MPH30 ? HS_MINB_MPH : HS_MI
   // divisions, the block reads them after the next barrier
   double* sc = red + 8;                                  // [dt, update factor, dx/dt]
   if (tid == 0) {
-    const double dt0 = g.cfl * g.dx / lam_cur;           // main.jl:212
+    const double dt0 = g.dt_shared ? *g.dt_shared : g.cfl * g.dx / lam_cur;   // main.jl:212 (dt_shared: a dimension-split sweep takes the grid's dt)
     const double lambda0 = g.dx / dt0;                   // main.jl:223
     sc[0] = dt0;
     sc[1] = (FLUX == FLUX_HLL) ? dt0 / g.dx : 1.0 / lambda0;   // main.jl:225,59 / :40
@@ -685,7 +686,7 @@ __device__ __forceinline__ void qp_step_body(const StepArgs& g, const double* Qi
   if (warp == QP_WARPS - 1 && ph == 0) { lo_s[l] = ld(aux_in + gi); hi_s[l] = ld(aux_in + g.stride + gi); }
   if (tid == 0) {
     const double lam_cur = ld(reinterpret_cast<const double*>(g.lam) + (size_t)cur * g.nprob + prob);
-    const double dt0 = g.cfl * g.dx / lam_cur;           // main.jl:212
+    const double dt0 = g.dt_shared ? *g.dt_shared : g.cfl * g.dx / lam_cur;   // main.jl:212 (dt_shared: a dimension-split sweep takes the grid's dt)
     const double lambda0 = g.dx / dt0;                   // main.jl:223
     sc[0] = dt0;
     sc[1] = (FLUX == FLUX_HLL) ? dt0 / g.dx : 1.0 / lambda0;   // main.jl:225,59 / :40
@@ -984,7 +985,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 
   auto write_scalars = [&](double* dst, unsigned long long lam_bits, double t) {
     const double lam_cur = __longlong_as_double((long long)lam_bits);
-    const double dt0 = g.cfl * g.dx / lam_cur;           // main.jl:212
+    const double dt0 = g.dt_shared ? *g.dt_shared : g.cfl * g.dx / lam_cur;   // main.jl:212 (dt_shared: a dimension-split sweep takes the grid's dt)
     const double lambda0 = g.dx / dt0;                   // main.jl:223
     dst[0] = dt0;
     dst[1] = (FLUX == FLUX_HLL) ? dt0 / g.dx : 1.0 / lambda0;   // main.jl:225,59 / :40
@@ -1632,6 +1633,63 @@ __global__ void __launch_bounds__(T) k_faceop(const double* __restrict__ Ql, con
   bad = __any_sync(FULL, valid ? bad : 0);
   if (bad && (tid & 31) == 0) atomicOr(status, 1);
   (void)J0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dimension-split 2-D stepping.  The physics is frame-indifferent (u -> R u, F -> R F; oracle anchor
+// "wave speeds rotate with the frame"), so a sweep along y IS the x-sweep applied to the state seen from a frame rotated by
+// R e_2 = e_1: R = [[0,1,0],[-1,0,0],[0,0,1]], i.e. a signed permutation of the components -- exact in floating point.
+// k_transpose_rot: per variable a tiled 2-D transpose ([rows][cols] -> [cols][rows], both coalesced through a padded
+// shared-memory tile) with that signed permutation folded in, so that the rows of the result are the grid's columns in the
+// rotated frame and the 1-D kernels run on them unchanged (as an ensemble of independent rows with one shared dt).
+// ------------------------------------------------------------------------------------------------
+struct RotMap { int src[30]; double sign[30]; int nvar; };
+__global__ void __launch_bounds__(256) k_transpose_rot(const double* __restrict__ in, double* __restrict__ out, int rows, int cols,
+                                                       const RotMap map) {
+  __shared__ double tile[32][33];
+  const int v = blockIdx.z;
+  const double* src = in + (size_t)map.src[v] * rows * cols;
+  double* dst = out + (size_t)v * rows * cols;
+  const double sg = map.sign[v];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[k][threadIdx.x] = src[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + threadIdx.x;      // out is [cols][rows]
+    if (r < rows && c < cols) dst[(size_t)c * rows + r] = sg * tile[threadIdx.x][k];
+  }
+}
+// dt = min(cfl dx / max_rows lambda_x, cfl dy / max_cols lambda_y), clock and step count of the 2-D grid; one block.
+// clock: [t, dt, steps (as double), lambda_x, lambda_y]
+__global__ void __launch_bounds__(256) k_dt2d(const unsigned long long* __restrict__ lam_x, int nlx, const unsigned long long* __restrict__ lam_y,
+                                              int nly, double cfl, double dx, double dy, double t_end, double* clock) {
+  __shared__ unsigned long long red[2][256];
+  unsigned long long mx = 0ull, my = 0ull;
+  for (int i = threadIdx.x; i < nlx; i += 256) mx = max(mx, lam_x[i]);     // non-negative doubles order like their bit patterns
+  for (int i = threadIdx.x; i < nly; i += 256) my = max(my, lam_y[i]);
+  red[0][threadIdx.x] = mx; red[1][threadIdx.x] = my;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      red[0][threadIdx.x] = max(red[0][threadIdx.x], red[0][threadIdx.x + s]);
+      red[1][threadIdx.x] = max(red[1][threadIdx.x], red[1][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double lx = __longlong_as_double((long long)red[0][0]), ly = __longlong_as_double((long long)red[1][0]);
+    const double dtx = cfl * dx / lx, dty = cfl * dy / ly;
+    const double t = clock[0];
+    const bool active = t < t_end;                 // while t < T, main.jl:202 (a finished grid takes dt = 0 sweeps: no-ops)
+    const double dt = active ? fmin(dtx, dty) : 0.0;
+    clock[1] = dt;
+    clock[0] = t + dt;
+    clock[2] += active ? 1.0 : 0.0;
+    clock[3] = lx; clock[4] = ly;
+  }
 }
 
 // self-test of the branch-free device math (hs_rcp / hs_rsqrt / hs_sqrt / largest eigenvalue) on caller data

@@ -10,7 +10,7 @@ import numpy as np
 from . import _lib as L
 from .testcases import riemann_grid
 
-__all__ = ["Solver", "initial_condition", "update_cell", "register_host", "unregister_host"]
+__all__ = ["Solver", "Solver2D", "initial_condition", "update_cell", "register_host", "unregister_host"]
 
 _FLUX = {"hll": L.HLL, "lxf": L.LXF, L.HLL: L.HLL, L.LXF: L.LXF}
 
@@ -128,6 +128,61 @@ class Solver:
         a, b = C.c_int64(0), C.c_int64(0)
         L.check(L.lib().hs_step_host_stats(self._ctx, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+
+class Solver2D:
+    """Dimension-split 2-D solver on an nx x ny grid (hs2d_*): Q^{n+1} = Y(dt) X(dt) Q^n with the 1-D step of
+    main.jl:204-227 along rows and columns, dt = cfl min(dx / max lambda_x, dy / max lambda_y).  Arrays are (ny, nx, nvar)
+    C-contiguous = Julia's Array{Float64,3}(nvar, nx, ny)."""
+
+    def __init__(self, eos, nx, ny, model=L.MPH30, device=0):
+        self.model, self.nvar, self.nx, self.ny = model, L.NVAR[model], int(nx), int(ny)
+        self._ctx = C.c_void_p()
+        self._eos = L.eos_array(eos, model)
+        L.check(L.lib().hs2d_create(C.byref(self._ctx), model, self._eos, L.NPHASE[model], self.nx, self.ny, int(device)))
+        self.t, self.steps = 0.0, 0
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            L.lib().hs2d_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def upload(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        if Q.shape != (self.ny, self.nx, self.nvar):
+            raise ValueError(f"expected {(self.ny, self.nx, self.nvar)}, got {Q.shape}")
+        L.check(L.lib().hs2d_upload(self._ctx, Q.ctypes.data))
+        self.t, self.steps = 0.0, 0
+        return self
+
+    def download(self):
+        Q = np.empty((self.ny, self.nx, self.nvar))
+        L.check(L.lib().hs2d_download(self._ctx, Q.ctypes.data))
+        return Q
+
+    def step(self, flux="hll", cfl=0.6, dx=None, dy=None):
+        dx = 1.0 / self.nx if dx is None else dx
+        dy = 1.0 / self.ny if dy is None else dy
+        dt = C.c_double(0.0)
+        L.check(L.lib().hs2d_step(self._ctx, _FLUX[flux], float(cfl), float(dx), float(dy), C.byref(dt)))
+        self.t += dt.value; self.steps += 1
+        return dt.value
+
+    def advance(self, t_end, flux="hll", cfl=0.6, dx=None, dy=None, max_steps=1 << 30):
+        dx = 1.0 / self.nx if dx is None else dx
+        dy = 1.0 / self.ny if dy is None else dy
+        t, n = C.c_double(0.0), C.c_int64(0)
+        L.check(L.lib().hs2d_advance(self._ctx, _FLUX[flux], float(cfl), float(dx), float(dy), float(t_end), int(max_steps), C.byref(t), C.byref(n)))
+        self.t, self.steps = t.value, int(n.value)
+        return self.steps
 
 
 def register_host(arr):

@@ -116,6 +116,25 @@ int hs_host_unregister(void* ptr);
 int hs_step_host_stats(hs_ctx_t* ctx, int64_t* pipelined_calls, int64_t* speculation_hits);
 
 /* ------------------------------------------------------------------------------------------
+ * Dimension-split 2-D solver on an nx x ny grid (the reference driver is 1-D, its physics takes a normal:
+ * EquationsOfState.jl:223, HyperelasticityMPh.jl:264).  Q^{n+1} = Y(dt) X(dt) Q^n with X / Y the 1-D step of main.jl:204-227
+ * along the grid rows / columns -- the y-sweep runs the same kernels on the state seen from the frame rotated by R e_2 = e_1
+ * (u -> R u, F -> R F: a signed permutation, exact) --, dt = cfl min(dx / max lambda_x, dy / max lambda_y).  Each sweep is the 1-D
+ * step on every grid line including its boundary rule (first / last cell of the line frozen, main.jl:219-220).
+ * Q: (nvar, nx, ny) column-major (cell (i, j) = record i + nx j).  A grid that is uniform in y reproduces the 1-D solver in every
+ * row (bit for bit, except that the two-phase HLL flux leaves ~1e-16 behind between equal states: its Q_hll is Q only to roundoff).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hs2d_ctx hs2d_ctx_t;
+int hs2d_create(hs2d_ctx_t** ctx, int model, const hs_barton2009_t* eos, int nphase, int64_t nx, int64_t ny, int device);
+int hs2d_destroy(hs2d_ctx_t* ctx);
+int hs2d_upload(hs2d_ctx_t* ctx, const double* Q);       /* also resets the clock */
+int hs2d_download(hs2d_ctx_t* ctx, double* Q);
+int hs2d_step(hs2d_ctx_t* ctx, int flux, double cfl, double dx, double dy, double* dt_out);
+/* steps while t < t_end (no clipping of the last step), at most max_steps; t_out / steps_out: clock of the grid since upload */
+int hs2d_advance(hs2d_ctx_t* ctx, int flux, double cfl, double dx, double dy, double t_end, int64_t max_steps, double* t_out,
+                 int64_t* steps_out);
+
+/* ------------------------------------------------------------------------------------------
  * Stateless batches: literal drop-ins for the per-cell / per-face Julia functions.
  * n = number of cells (faces).  device = CUDA device ordinal.
  * ------------------------------------------------------------------------------------------ */

@@ -19,7 +19,7 @@ module HyperelasticB200
 export Barton2009, Hank2016, energy, pressure, stress, prim2cons_mph, cons2prim_mph, flux_mph, noncons_flux, get_eigvals, lxf, hll,
        initial_states, initial_condition, initial_condition_tanh, update_cell,
        Solver, upload!, download!, step!, step_host!, advance!, set_time!, wave_speeds, destroy!, host_register!, host_unregister!,
-       SinglePhase
+       SinglePhase, Solver2D
 
 const LIB = get(ENV, "HYPERELASTIC_B200_LIB", joinpath(@__DIR__, "..", "hyperelasticsolver_b200", "libhyperelastic_b200.so"))
 
@@ -282,6 +282,34 @@ function advance!(s::Solver, flux::Function, cfl, dx, T; t=0.0, step_num=0, max_
       (Ptr{Cvoid}, Cint, Float64, Float64, Float64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
       s.ctx, flux === hll ? HS_FLUX_HLL : HS_FLUX_LXF, cfl, dx, T, max_steps, tv, sv, C_NULL))
   return s.nprob == 1 ? (tv[1], sv[1]) : (tv, sv)
+end
+
+# --- dimension-split 2-D solver (hs2d_*; the reference driver is 1-D, its physics takes a normal) ----------------
+# Q::Array{Float64,3}(nvar, nx, ny); every sweep is the 1-D step of main.jl:204-227 along the grid lines
+mutable struct Solver2D
+  ctx::Ptr{Cvoid}
+  nvar::Int; nx::Int; ny::Int
+end
+function Solver2D(eos::Tuple{Barton2009,Barton2009}, nx::Integer, ny::Integer; device::Integer=0)
+  ref = Ref{Ptr{Cvoid}}(C_NULL); e = eosvec(eos)
+  GC.@preserve e check(ccall((:hs2d_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Barton2009}, Cint, Int64, Int64, Cint),
+      ref, HS_MODEL_MPH30, e, 2, nx, ny, device))
+  s = Solver2D(ref[], 30, nx, ny)
+  finalizer(x -> (x.ctx != C_NULL && ccall((:hs2d_destroy, LIB), Cint, (Ptr{Cvoid},), x.ctx); x.ctx = C_NULL), s)
+  return s
+end
+upload!(s::Solver2D, Q::Array{Float64,3}) = GC.@preserve Q check(ccall((:hs2d_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), s.ctx, Q))
+download!(s::Solver2D, Q::Array{Float64,3}) = (GC.@preserve Q check(ccall((:hs2d_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), s.ctx, Q)); Q)
+function step!(s::Solver2D, flux::Function, cfl, dx, dy)
+  dt = Ref{Float64}(0.0)
+  check(ccall((:hs2d_step, LIB), Cint, (Ptr{Cvoid}, Cint, Float64, Float64, Float64, Ref{Float64}), s.ctx, flux === hll ? HS_FLUX_HLL : HS_FLUX_LXF, cfl, dx, dy, dt))
+  return dt[]
+end
+function advance!(s::Solver2D, flux::Function, cfl, dx, dy, T; max_steps=typemax(Int32))
+  t = Ref{Float64}(0.0); n = Ref{Int64}(0)
+  check(ccall((:hs2d_advance, LIB), Cint, (Ptr{Cvoid}, Cint, Float64, Float64, Float64, Float64, Int64, Ref{Float64}, Ref{Int64}),
+      s.ctx, flux === hll ? HS_FLUX_HLL : HS_FLUX_LXF, cfl, dx, dy, T, max_steps, t, n))
+  return t[], n[]
 end
 
 # --- Hank2016 (EquationsOfState.jl:317-356): scalar methods like the reference, batched over columns ------------

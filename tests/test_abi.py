@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     txt = open(os.path.join(ROOT, "include", "hyperelastic_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(hsd?_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(hs(?:d|2d)?_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_symbols_exported(hs):
