@@ -96,7 +96,9 @@ def test_pipeline_generic_exponents(gpu):
     assert np.allclose(h, href, rtol=1e-14, atol=0) and _close(Q, ref, 1e-14)
 
 
-@pytest.mark.parametrize("nx,nprob", [(301, 9), (300, 9), (4096, 40), (125, 33), (3, 5)])
+# (301, 8) / (7, 300): ODD problem length with an EVEN total -- tiles start on odd columns there, which the tensor-map copies
+# cannot do (16-byte alignment of the box start): the launcher must pick the row copies (an illegal-instruction fault before round 2)
+@pytest.mark.parametrize("nx,nprob", [(301, 9), (300, 9), (4096, 40), (125, 33), (3, 5), (301, 8), (7, 300)])
 def test_pipeline_ensembles_with_different_stopping_steps(gpu, nx, nprob):
     hs = gpu
     eos = hs.Barton2009()
