@@ -140,7 +140,7 @@ bool make_tile_map(CUtensorMap* m, const double* base, long long width, long lon
 // Single-phase TMA tile pipeline (k_step_sp): every block walks over `kper` tiles.
 template <int FLUX, bool GEN, int T, bool SINGLE, bool TM2D>
 int launch_step_sp_s(const StepArgs& a, int64_t ntiles, int kper, const CUtensorMap& mq, const CUtensorMap& ma, cudaStream_t st) {
-  constexpr size_t smem = step_sp_smem_bytes<T>();
+  constexpr size_t smem = step_sp_smem_bytes<T, TM2D>();
   static std::atomic<unsigned> attr_dev_mask{0};   // (the attribute is per device and per kernel instantiation)
   int dev = 0;
   CU(cudaGetDevice(&dev));

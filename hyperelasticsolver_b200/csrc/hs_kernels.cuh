@@ -956,8 +956,18 @@ constexpr int SP_NST = 13 + SP_NAX;              // rows per stage: 13 state row
 constexpr unsigned SP_ROW_BYTES = SP_TS * 8, SP_STAGE_BYTES = SP_NST * SP_ROW_BYTES;
 // SP13 variable stored in record slot j (inverse of sp_slot)
 __host__ __device__ constexpr int sp_var(int j) { return j < 5 ? j - 2 : (j == 5 ? 12 : 3 + 3 * ((j - 6) % 3) + (j - 6) / 3); }
-template <int T> constexpr size_t step_sp_smem_bytes() {
-  return sizeof(double) * (2 * SP_NST * SP_TS + 2 * (T / 32) * 13 + T / 32 + 24 + 2);
+// shared-memory stages of the tensor-map flavour (tile k + HS_SP_STAGES - 1 is in flight while tile k is computed); the
+// row-copy flavour always has two
+#ifndef HS_SP_STAGES
+#define HS_SP_STAGES 2
+#endif
+template <bool TM2D> __host__ __device__ constexpr int sp_stages() { return TM2D ? HS_SP_STAGES : 2; }
+template <int T, bool TM2D> __host__ __device__ constexpr size_t sp_stage_doubles() {
+  return (size_t)sp_stages<TM2D>() * SP_NST * (TM2D ? T : SP_TS) > (size_t)2 * SP_NST * SP_TS ? (size_t)sp_stages<TM2D>() * SP_NST * (TM2D ? T : SP_TS)
+                                                                                             : (size_t)2 * SP_NST * SP_TS;
+}
+template <int T, bool TM2D = false> constexpr size_t step_sp_smem_bytes() {
+  return sizeof(double) * (sp_stage_doubles<T, TM2D>() + 2 * (T / 32) * 13 + T / 32 + 24 + 4);
 }
 
 // SINGLE: one problem (nprob == 1, every grid config): the problem index, the per-problem scalars, the column parities
@@ -972,12 +982,13 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   static_assert(T == 128, "stage rows hold 128 cells");
   constexpr int TS = TM2D ? T : SP_TS;          // doubles per stage row
   constexpr int STAGE = SP_NST * TS;            // doubles per stage
+  constexpr int NSTG = sp_stages<TM2D>(), PD = NSTG - 1;         // stages, prefetch distance in tiles
   extern __shared__ __align__(128) double smem[];
-  double* const stage0 = smem;                                   // [2][SP_NST][SP_TS]
-  double* const Hb = smem + 2 * SP_NST * SP_TS;                  // [2][T/32][13] face flux of lane 0 of every warp (same place for both stage widths)
+  double* const stage0 = smem;                                   // [NSTG][SP_NST][TS]
+  double* const Hb = smem + sp_stage_doubles<T, TM2D>();         // [2][T/32][13] face flux of lane 0 of every warp
   double* const red = Hb + 2 * (T / 32) * 13;                    // [T/32]
   double* const sc = red + T / 32;                               // [3][8]: dt, update factor, dx/dt, t, lambda_max
-  uint64_t* const mbar = reinterpret_cast<uint64_t*>(sc + 24);   // [2]
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(sc + 24);   // [NSTG]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned ntiles = (unsigned)g.tiles_per_prob * (unsigned)g.nprob;
@@ -1027,12 +1038,29 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   long long off = (long long)prob * g.ncells + (long long)tile * (T - 2);
   bool cur_tma = TM2D || off + SP_TS <= g.stride;
   if (tid == 0) {
-    tma::mbar_init(&mbar[0], 1);
-    tma::mbar_init(&mbar[1], 1);
+#pragma unroll
+    for (int i = 0; i < NSTG; ++i) tma::mbar_init(&mbar[i], 1);
     tma::fence_mbar_init();
   }
   __syncthreads();
+  // start column of the tile d places after the current one in this block's sequence (false: there is none)
+  auto tile_after = [&](int kk, int d, unsigned id_, int prob_, int tile_, long long& offd) -> bool {
+    const unsigned idd = id_ + (unsigned)d * id_step;
+    if (kk + d >= kper || idd >= ntiles) return false;
+    if (SINGLE) { offd = (long long)((int)idd * (T - 2)); return true; }
+    int td = tile_ + d, pd = prob_;
+    while (td >= g.tiles_per_prob) { td -= g.tiles_per_prob; ++pd; }
+    offd = (long long)pd * g.ncells + (long long)td * (T - 2);
+    return true;
+  };
   if (cur_tma) issue(off, stage0, &mbar[0]);
+  if (NSTG > 2) {   // deeper pipeline: tiles 1 .. PD-1 of this block are requested up front as well
+#pragma unroll
+    for (int d = 1; d < PD; ++d) {
+      long long offd = 0;
+      if (tile_after(0, d, id, prob, tile, offd)) issue(offd, stage0 + d * STAGE, &mbar[d]);
+    }
+  }
   // the per-problem scalars (three IEEE divisions) are the job of one thread of warp 1, and only when the problem changes
   if (tid == 32) write_scalars(sc, __ldg(g.lam + (size_t)g.cur * g.nprob + prob), __ldg(g.tt + (size_t)g.cur * g.nprob + prob));
   __syncthreads();
@@ -1043,7 +1071,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   double lam_run = 0.0;
   int bad = 0;
   for (int k = 0; k < kper; ++k) {
-    const int s = k & 1;
+    const int s = NSTG == 2 ? (k & 1) : k % NSTG;
     double* const st = stage0 + s * STAGE;
     const double* const scv = sc + (SINGLE ? 0 : sci * 8);
     // ---- start fetching the next tile of this block ---------------------------------------------
@@ -1063,8 +1091,14 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       }
       next_tma = TM2D || offn + SP_TS <= g.stride;
     }
-    // (every thread passed the barrier of tile k-1, after which nobody reads stage s^1 any more)
-    if (next_tma) issue(offn, stage0 + (s ^ 1) * STAGE, &mbar[s ^ 1]);
+    // (every thread passed the barrier of tile k-1, after which nobody reads the stage of tile k-1 any more: it takes tile k+PD)
+    if (NSTG == 2) {
+      if (next_tma) issue(offn, stage0 + (s ^ 1) * STAGE, &mbar[s ^ 1]);
+    } else {
+      long long offp = 0;
+      const int sp = (k + PD) % NSTG;
+      if (tile_after(k, PD, id, prob, tile, offp)) issue(offp, stage0 + sp * STAGE, &mbar[sp]);
+    }
     const bool new_prob = !SINGLE && has_next && probn != prob;
     unsigned long long lam_n = 0ull;
     double t_n = 0.0;
