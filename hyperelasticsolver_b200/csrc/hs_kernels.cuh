@@ -977,7 +977,7 @@ template <int T, bool TM2D = false> constexpr size_t step_sp_smem_bytes() {
 // issue slots per warp and tile, no column parities, no thread-loaded last tile.  Needs an even stride (row pitch multiple of
 // 16 bytes) and a stride below 2^31; the host falls back to the row copies otherwise.
 template <int FLUX, bool GEN, int T, bool SINGLE, bool TM2D>
-__global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, const int kper, const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, const int kper, const int bpp, const __grid_constant__ CUtensorMap tmQ,
                                                            const __grid_constant__ CUtensorMap tmA) {
   static_assert(T == 128, "stage rows hold 128 cells");
   constexpr int TS = TM2D ? T : SP_TS;          // doubles per stage row
@@ -1029,12 +1029,19 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     }
   };
 
-  // One grid: block b takes tiles b, b + gridDim, ... (blocks resident at the same time work on neighbouring tiles).
-  // Ensembles: block b takes the kper consecutive tiles from b * kper, so that it changes problem (new scalars, one
-  // more barrier for the max(lambda) flush) at most every tiles_per_prob tiles instead of at every tile.
-  unsigned id = SINGLE ? blockIdx.x : blockIdx.x * (unsigned)kper;
-  const unsigned id_step = SINGLE ? gridDim.x : 1u;
-  int prob = SINGLE ? 0 : (int)(id / (unsigned)g.tiles_per_prob), tile = SINGLE ? (int)id : (int)(id % (unsigned)g.tiles_per_prob);
+  // SINGLE (the problem is a block invariant): bpp blocks share one problem, block b of them takes its tiles b, b + bpp, ...
+  // (blocks resident at the same time work on neighbouring tiles); one grid is the case bpp = gridDim.  Since round 2 ensembles of
+  // problems with at least a few tiles run this way too (bpp = ceil(tiles_per_prob / 8) blocks per problem): the per-problem
+  // indexing of the other flavour cost ~110 instructions per cell-update (ncu: 1150 vs 1039).
+  // !SINGLE (ensembles of tiny problems): block b takes the kper consecutive tiles from b * kper across problem boundaries (new
+  // scalars and one more barrier for the max(lambda) flush whenever the problem changes).
+  int prob = SINGLE ? (int)(blockIdx.x / (unsigned)bpp) : 0;
+  unsigned id = SINGLE ? blockIdx.x - (unsigned)prob * (unsigned)bpp : blockIdx.x * (unsigned)kper;
+  const unsigned id_step = SINGLE ? (unsigned)bpp : 1u;
+  if (!SINGLE) prob = (int)(id / (unsigned)g.tiles_per_prob);
+  int tile = SINGLE ? (int)id : (int)(id % (unsigned)g.tiles_per_prob);
+  const int pbase = SINGLE ? prob * g.ncells : 0;          // first cell of the block's problem (< 2^31: hsd_problem_init)
+  const unsigned nt_lim = SINGLE ? (unsigned)g.tiles_per_prob : ntiles;
   long long off = (long long)prob * g.ncells + (long long)tile * (T - 2);
   bool cur_tma = TM2D || off + SP_TS <= g.stride;
   if (tid == 0) {
@@ -1046,8 +1053,8 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
   // start column of the tile d places after the current one in this block's sequence (false: there is none)
   auto tile_after = [&](int kk, int d, unsigned id_, int prob_, int tile_, long long& offd) -> bool {
     const unsigned idd = id_ + (unsigned)d * id_step;
-    if (kk + d >= kper || idd >= ntiles) return false;
-    if (SINGLE) { offd = (long long)((int)idd * (T - 2)); return true; }
+    if (kk + d >= kper || idd >= nt_lim) return false;
+    if (SINGLE) { offd = (long long)(pbase + (int)idd * (T - 2)); return true; }
     int td = tile_ + d, pd = prob_;
     while (td >= g.tiles_per_prob) { td -= g.tiles_per_prob; ++pd; }
     offd = (long long)pd * g.ncells + (long long)td * (T - 2);
@@ -1076,14 +1083,14 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     const double* const scv = sc + (SINGLE ? 0 : sci * 8);
     // ---- start fetching the next tile of this block ---------------------------------------------
     const unsigned idn = id + id_step;
-    const bool has_next = (k + 1 < kper) && idn < ntiles;
+    const bool has_next = (k + 1 < kper) && idn < nt_lim;
     int probn = prob, tilen = 0;
     long long offn = 0;
     bool next_tma = false;
     if (has_next) {
       if (SINGLE) {
         tilen = (int)idn;
-        offn = (long long)(tilen * (T - 2));          // < ncells < 2^31
+        offn = (long long)(pbase + tilen * (T - 2));  // < ncells * nprob < 2^31
       } else {
         tilen = tile + 1;
         if (tilen >= g.tiles_per_prob) { tilen = 0; ++probn; }
@@ -1109,8 +1116,10 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
 
     const int c = tile * (T - 2) + tid;
     const bool valid = c < g.ncells;
-    const long long gi = (long long)prob * g.ncells + (valid ? c : g.ncells - 1);
-    const int pe = SINGLE ? 0 : (int)(off & 1), po = SINGLE ? (int)(g.stride & 1) : (int)((off + g.stride) & 1);   // (tile starts are even)
+    // (32-bit cell index: ncells * nprob < 2^31 is guaranteed by hsd_problem_init, and a 32-bit index lets every global access be one
+    // wide multiply-add on a uniform row base -- the ensemble flavour spent ~100 instructions per cell-update on 64-bit indexing)
+    const int gi = prob * g.ncells + (valid ? c : g.ncells - 1);
+    const int pe = SINGLE ? (pbase & 1) : (int)(off & 1), po = SINGLE ? (int)((pbase + g.stride) & 1) : (int)((off + g.stride) & 1);   // (tiles start on even cells of their problem)
     // slot j / cache row r of the cell in stage column `col`
     // (row copies: stage row = slot - 2, column shifted by the row's parity; tensor-map copies: stage row = variable, no shift)
 #define SQ(j, col) st[(TM2D ? sp_var(j) : (j) - 2) * TS + (col) + (TM2D ? 0 : ((sp_var(j) & 1) ? po : pe))]
@@ -1277,7 +1286,7 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
     if (!has_next) break;
     if (new_prob) sci = (sci + 1) % 3;
     id = idn; tile = tilen; cur_tma = next_tma;
-    if (SINGLE) off = (long long)(tile * (T - 2));
+    if (SINGLE) off = (long long)(pbase + tile * (T - 2));
     else { prob = probn; off = offn; }
   }
 }
