@@ -63,6 +63,9 @@ def test_problem_init_and_arg_errors(hs):
     assert lib.hsd_problem_init(C.byref(p), 7, eos2, 2, 1000, 1) == L.HS_ERR_ARG
     assert lib.hsd_problem_init(C.byref(p), L.MPH30, eos2, 2, 2, 1) == L.HS_ERR_ARG
     assert b"ncells" in lib.hs_last_error()
+    # the kernels index cells with 32 bits: 65 536 x 4 096 = 2^28 is fine, 2^31 cells are not (more than one device holds anyway)
+    assert lib.hsd_problem_init(C.byref(p), L.MPH30, eos2, 2, 4096, 65536) == 0 and p.stride == 1 << 28
+    assert lib.hsd_problem_init(C.byref(p), L.MPH30, eos2, 2, 1 << 16, 1 << 15) == L.HS_ERR_ARG
     with pytest.raises(ValueError):
         L.eos_array((hs.Barton2009(),), L.MPH30)
 
