@@ -95,8 +95,9 @@ def numa_local_affinity(dev_index):
                              capture_output=True, text=True, timeout=20).stdout.strip().lower()
         bus = bus[-12:] if len(bus) > 12 else bus          # 00000000:1b:00.0 -> 0000:1b:00.0
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
-        if node < 0:
-            return None
+        if node < 0:   # (virtualised hosts expose one node and no device affinity: nothing to bind)
+            nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+            return f"not exposed by the host ({len(nodes)} NUMA node(s) visible)"
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
