@@ -11,7 +11,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _problem(hs, model, nx):
-    if model == "mph30":
+    if model == "mph30-hetero":      # different equations of state per phase, generic exponents (main.jl:133)
+        eos = (hs.Barton2009(), hs.Barton2009(_rho0=8.93, _c0=6.22, _cv=9.0e-4, _t0=300, _b0=3.16, _alpha=1, _beta=3.577, _gamma=2.088))
+        Ql, Qr = hs.initial_states(eos, 7); hm = hs.MPH30
+    elif model == "mph30":
         eos = (hs.Barton2009(), hs.Barton2009()); Ql, Qr = hs.initial_states(eos, 6); hm = hs.MPH30
     else:
         eos = hs.Barton2009(); Ql, Qr = hs.hyperelasticity.initial_states(eos, 1); hm = hs.SP13
@@ -33,7 +36,7 @@ def small_chunks():
 
 
 @pytest.mark.parametrize("model,nx,flux", [("sp13", 20000, "hll"), ("sp13", 6146, "lxf"), ("sp13", 4096, "hll"),
-                                           ("mph30", 9000, "hll"), ("mph30", 4100, "lxf")])
+                                           ("mph30", 9000, "hll"), ("mph30", 4100, "lxf"), ("mph30-hetero", 5000, "hll")])
 def test_pipelined_step_host_bit_identical(gpu, small_chunks, model, nx, flux):
     hs = gpu
     eos, hm, Q0 = _problem(hs, model, nx)
