@@ -422,15 +422,17 @@ class Bench:
         if c["ensemble"]:
             nprob_e = min(wl["nprob"], (1 << 24) // wl["cells"] * world)
             pe0, pe1 = nprob_e * rank // world, nprob_e * (rank + 1) // world
-            sol = EnsembleSolver(kern, wl["cells"], nprob_e)
-            e_cells_local, e_units = sol.nprob * wl["cells"], nprob_e * wl["cells"]
+            np_loc = pe1 - pe0
+            s2 = H.Solver(c["eos"], wl["cells"], nprob=np_loc, model=c["hmodel"], device=self.local)   # every rank steps its own share: no exchange
+            e_cells_local, e_units = np_loc * wl["cells"], nprob_e * wl["cells"]
             host_in = torch.empty(e_cells_local, nvar, dtype=torch.float64, pin_memory=True)
             host_out = torch.empty_like(host_in).pin_memory()
             left_h = (torch.arange(wl["cells"]) < wl["cells"] / 2)[None, :, None]
-            q = torch.as_tensor(c["Qlr"][: pe1 - pe0])
-            host_in.view(sol.nprob, wl["cells"], nvar)[:] = torch.where(left_h, q[:, None, 0, :], q[:, None, 1, :])
-            step_host = lambda a, b: sol.step_host(a, b, flux, 0.6, c["dx"])
-            api = "EnsembleSolver.step_host: pinned host state -> device, CFL sweep, fused step, device -> host, every step"
+            q = torch.as_tensor(c["Qlr"][:np_loc])
+            host_in.view(np_loc, wl["cells"], nvar)[:] = torch.where(left_h, q[:, None, 0, :], q[:, None, 1, :])
+            step_host = lambda a, b: s2.step_host(a.numpy().reshape(np_loc, wl["cells"], nvar), b.numpy().reshape(np_loc, wl["cells"], nvar), "hll", 0.6, c["dx"])
+            api = ("hs_step_host (C ABI) on this rank's share of the problems: chunk-pipelined by groups of whole problems "
+                   "(H2D || CFL sweep + fused step || D2H, per-problem speculative dt)")
         else:
             e_cells = min(wl["cells"] if wl["scaling"] == "weak" else wl["cells"] // world, 1 << 24)
             e_units = e_cells * world
@@ -535,8 +537,8 @@ class Bench:
         m = self.resident(c, steps, warmup)
         r = {"value": m["value"], "unit": UNIT, "ms_per_step": m["ms_per_step"], "steps": steps, "warmup": warmup, "scaling": c["wl"]["scaling"],
              "config": workload_config(name, self.world), "exchange": c["exchange"], "roofline": self.roofline(c, m), "gpu_launches": m["launches"]}
-        if name == "mph30_2p24" and self.world == 1:
-            # the model main.jl ships, end to end with the state in host memory (2 x 4.03 GB over the link per step)
+        if name in ("mph30_2p24", "ensemble_sp") and self.world == 1:
+            # end to end with the state in host memory: the model main.jl ships (2 x 4.03 GB over the link per step) / a 2^24-cell sample of the ensemble
             c.pop("sol")
             self.torch.cuda.empty_cache()
             r["e2e"] = self.e2e(c, 3)

@@ -1,6 +1,7 @@
 // C ABI of libhyperelastic_b200.so (see include/hyperelastic_b200.h for the contract and the
 // reference interfaces each entry point replaces).  Host side only: argument checks, device
 // memory, launches.  There is no CPU compute path in this file by design.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -491,6 +492,8 @@ struct Part {                 // one slab (or one share of an ensemble) on one d
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   double* stage_out = nullptr;
   double* scal_sweep = nullptr;
+  double* scal_win = nullptr;     // ensembles: per-chunk scalar blocks of the speculative steps and of the sweeps
+  size_t scal_win_doubles = 0;
   std::vector<cudaEvent_t> ev_in, ev_out;
 };
 }  // namespace
@@ -614,7 +617,7 @@ int hs_destroy(hs_ctx_t* c) {
   for (auto& p : c->parts) {
     DeviceGuard g(p.device);
     for (int k = 0; k < 2; ++k) { cudaFree(p.Q[k]); cudaFree(p.aux[k]); }
-    cudaFree(p.scal); cudaFree(p.stage); cudaFree(p.mbox); cudaFree(p.dt_hist); cudaFree(p.stage_out); cudaFree(p.scal_sweep);
+    cudaFree(p.scal); cudaFree(p.stage); cudaFree(p.mbox); cudaFree(p.dt_hist); cudaFree(p.stage_out); cudaFree(p.scal_sweep); cudaFree(p.scal_win);
     for (auto e : p.ev_in) cudaEventDestroy(e);
     for (auto e : p.ev_out) cudaEventDestroy(e);
     if (p.s_h2d) cudaStreamDestroy(p.s_h2d);
@@ -1079,6 +1082,122 @@ static int step_host_pipelined(hs_ctx_t* c, int flux, double cfl, double dx, con
   return st_sweep ? fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError") : HS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same pipeline for an ENSEMBLE on one device: a chunk is a group of whole problems (no ghost cells: problems are independent),
+// the hints are the per-problem max(lambda) of the state the previous call returned, and every group steps on its own compact
+// scalar block (the kernels index the per-problem scalars by the problem's position inside the launch).  All nprob true values are
+// compared with the hints at the end; any mismatch redoes the whole step on the device.
+// ---------------------------------------------------------------------------------------------
+static int step_host_pipelined_ensemble(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin, double* Qout, double* dt_out) {
+  Part& p = c->parts[0];
+  PART_ENTER(p);
+  const int64_t NC = c->ncells, NP = c->nprob, nvar = c->nvar;
+  int64_t G = host_chunk_cells() / NC;          // problems per chunk
+  if (G < 1) G = 1;
+  const int K = (int)((NP + G - 1) / G);
+  int rc = ensure_pipeline(c, p, K); if (rc) return rc;
+  rc = ensure_hist(c, 1); if (rc) return rc;
+  // two compact scalar blocks per chunk (step, sweep)
+  const size_t blk = (size_t)HS_SCAL_DOUBLES(G);
+  if (p.scal_win_doubles < 2 * blk * K) {
+    if (p.scal_win) { cudaFree(p.scal_win); p.scal_win = nullptr; }
+    CU(cudaMalloc(&p.scal_win, sizeof(double) * 2 * blk * K));
+    p.scal_win_doubles = 2 * blk * K;
+  }
+  const bool spec = c->has_state;
+  c->has_state = false;
+  const int cur_main = (int)(c->n % 3);
+  CU(cudaMemsetAsync(p.scal_win, 0, sizeof(double) * 2 * blk * K, p.stream));
+  // hints: the context's current max(lambda) slot, problem by problem, into slot 0 of the groups' step blocks
+  if (spec) {
+    for (int i = 0; i < K; ++i) {
+      const int64_t p0 = (int64_t)i * G, g = std::min<int64_t>(G, NP - p0);
+      CU(cudaMemcpyAsync(p.scal_win + (size_t)(2 * i) * blk, hsd_scal_lambda_cur(p.scal, NP, c->n) + p0, sizeof(double) * g, cudaMemcpyDeviceToDevice, p.stream));
+    }
+  }
+  std::vector<double> hint(NP, 0.0), truth(NP, 0.0);
+  if (spec) CU(cudaMemcpyAsync(hint.data(), p.scal + (size_t)cur_main * NP, sizeof(double) * NP, cudaMemcpyDeviceToHost, p.stream));
+  cudaEvent_t ev0 = p.ev_out[0];
+  CU(cudaEventRecord(ev0, p.stream));
+  CU(cudaStreamWaitEvent(p.s_h2d, ev0, 0));
+  const size_t cellb = (size_t)nvar * sizeof(double);
+  for (int i = 0; i < K; ++i) {
+    const int64_t p0 = (int64_t)i * G, g = std::min<int64_t>(G, NP - p0), c0 = p0 * NC, nc = g * NC;
+    double* sstep = p.scal_win + (size_t)(2 * i) * blk;
+    double* ssweep = sstep + blk;
+    CU(cudaMemcpyAsync(p.stage + c0 * nvar, Qin + c0 * nvar, (size_t)nc * cellb, cudaMemcpyHostToDevice, p.s_h2d));
+    CU(cudaEventRecord(p.ev_in[i], p.s_h2d));
+    CU(cudaStreamWaitEvent(p.stream, p.ev_in[i], 0));
+    rc = transpose_range(c->model, true, p.stage + c0 * nvar, p.Q[0] + c0, nc, p.prob.stride, p.stream); if (rc) return rc;
+    hsd_problem_t w = p.prob;   // g problems of NC cells, rows still `stride` apart
+    w.nprob = g;
+    rc = wave_bounds_impl(&w, p.Q[0] + c0, p.aux[0] + c0, ssweep, 0, nullptr, p.stream); if (rc) return rc;
+    if (spec) {
+      rc = hsd_step(&w, flux, cfl, dx, 1.0e300, 0, p.Q[0] + c0, p.aux[0] + c0, p.Q[1] + c0, p.aux[1] + c0, sstep, p.dt_hist + p0, 0, 1, 0, p.stream);
+      if (rc) return rc;
+      rc = transpose_range(c->model, false, p.Q[1] + c0, p.stage_out + c0 * nvar, nc, p.prob.stride, p.stream); if (rc) return rc;
+      CU(cudaEventRecord(p.ev_out[i], p.stream));
+      CU(cudaStreamWaitEvent(p.s_d2h, p.ev_out[i], 0));
+      CU(cudaMemcpyAsync(Qout + c0 * nvar, p.stage_out + c0 * nvar, (size_t)nc * cellb, cudaMemcpyDeviceToHost, p.s_d2h));
+    }
+  }
+  for (int i = 0; i < K; ++i) {   // (after the loop: a copy into pageable memory would stall the enqueueing thread at every chunk)
+    const int64_t p0 = (int64_t)i * G, g = std::min<int64_t>(G, NP - p0);
+    CU(cudaMemcpyAsync(truth.data() + p0, p.scal_win + (size_t)(2 * i + 1) * blk, sizeof(double) * g, cudaMemcpyDeviceToHost, p.stream));
+  }
+  CU(cudaStreamSynchronize(p.stream));
+  c->pipelined_calls += 1;
+  int st_all = 0;
+  bool same = spec && std::memcmp(hint.data(), truth.data(), sizeof(double) * NP) == 0;
+  // status words of the groups' blocks
+  {
+    std::vector<int> stw(2 * K, 0);
+    for (int i = 0; i < 2 * K; ++i) {
+      const int64_t g = std::min<int64_t>(G, NP - (int64_t)(i / 2) * G);
+      CU(cudaMemcpyAsync(&stw[i], scal_status(p.scal_win + (size_t)i * blk, g), sizeof(int), cudaMemcpyDeviceToHost, p.stream));
+    }
+    CU(cudaStreamSynchronize(p.stream));
+    for (int i = 0; i < 2 * K; ++i) if (same || (i & 1)) st_all |= stw[i];
+  }
+  CU(cudaMemsetAsync(p.scal, 0, sizeof(double) * HS_SCAL_DOUBLES(NP), p.stream));
+  if (same) {
+    // assemble the context's scalar block as upload + one step leave it: slot 1 = max(lambda) of the new states, t = dt, one step
+    for (int i = 0; i < K; ++i) {
+      const int64_t p0 = (int64_t)i * G, g = std::min<int64_t>(G, NP - p0);
+      double* sstep = p.scal_win + (size_t)(2 * i) * blk;
+      CU(cudaMemcpyAsync(p.scal + (size_t)1 * NP + p0, sstep + (size_t)1 * g, sizeof(double) * g, cudaMemcpyDeviceToDevice, p.stream));                 // lambda slot 1
+      CU(cudaMemcpyAsync(scal_t(p.scal, NP) + (size_t)1 * NP + p0, scal_t(sstep, g) + (size_t)1 * g, sizeof(double) * g, cudaMemcpyDeviceToDevice, p.stream));   // t slot 1
+      CU(cudaMemcpyAsync(scal_steps(p.scal, NP) + p0, scal_steps(sstep, g), sizeof(long long) * g, cudaMemcpyDeviceToDevice, p.stream));
+    }
+    if (dt_out) CU(cudaMemcpyAsync(dt_out, p.dt_hist, sizeof(double) * NP, cudaMemcpyDeviceToHost, p.stream));
+    CU(cudaStreamSynchronize(p.stream));
+    CU(cudaStreamSynchronize(p.s_d2h));
+    c->n = 1;
+    c->has_state = true;
+    c->speculation_hits += 1;
+  } else {
+    if (spec) CU(cudaStreamSynchronize(p.s_d2h));
+    CU(cudaMemcpyAsync(p.scal, truth.data(), sizeof(double) * NP, cudaMemcpyHostToDevice, p.stream));   // slot 0 = true max(lambda) per problem
+    c->n = 0;
+    rc = enqueue_step(c, flux, cfl, dx, 1.0e300, 0, 1); if (rc) return rc;
+    if (dt_out) CU(cudaMemcpyAsync(dt_out, p.dt_hist, sizeof(double) * NP, cudaMemcpyDeviceToHost, p.stream));
+    for (int i = 0; i < K; ++i) {
+      const int64_t p0 = (int64_t)i * G, g = std::min<int64_t>(G, NP - p0), c0 = p0 * NC, nc = g * NC;
+      rc = transpose_range(c->model, false, p.Q[1] + c0, p.stage_out + c0 * nvar, nc, p.prob.stride, p.stream); if (rc) return rc;
+      CU(cudaEventRecord(p.ev_out[i], p.stream));
+      CU(cudaStreamWaitEvent(p.s_d2h, p.ev_out[i], 0));
+      CU(cudaMemcpyAsync(Qout + c0 * nvar, p.stage_out + c0 * nvar, (size_t)nc * cellb, cudaMemcpyDeviceToHost, p.s_d2h));
+    }
+    CU(cudaStreamSynchronize(p.stream));
+    CU(cudaStreamSynchronize(p.s_d2h));
+    c->has_state = true;
+    const int rs = read_status(c);
+    if (rs) return rs;
+  }
+  if (st_all & 4) return fail(HS_ERR_CUDA, "tile copy (TMA) did not complete: internal error of the single-phase step kernel");
+  return st_all ? fail(HS_ERR_DOMAIN, "unphysical state (negative det / NaN): Julia would throw DomainError") : HS_OK;
+}
+
 int hs_step_host(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin, double* Qout, double* dt_out) {
   if (!c) return fail(HS_ERR_ARG, "null context");
   if (!Qin || !Qout) return fail(HS_ERR_ARG, "null Q");
@@ -1088,11 +1207,12 @@ int hs_step_host(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin
   // one grid on one device with at least two chunks: the pipelined form; everything else (ensembles, several devices,
   // small grids, odd cell counts) takes upload + step + download
   const bool pipe = !off && c->parts.size() == 1 && c->nprob == 1 && c->ncells % 2 == 0 && c->ncells >= host_chunk_cells() / 2 && c->ncells >= 4096;
-  if (!pipe) {
-    const int rc = step_host_plain(c, flux, cfl, dx, Qin, Qout, dt_out);
-    return rc;
-  }
-  return step_host_pipelined(c, flux, cfl, dx, Qin, Qout, dt_out);
+  // an ensemble on one device: groups of whole problems, at least two groups (even problem length keeps the groups on the tensor-map copies)
+  const bool pipe_ens = !off && c->parts.size() == 1 && c->nprob > 1 && c->ncells % 2 == 0 && c->ncells * c->nprob >= 4096 &&
+                        c->ncells * c->nprob >= 2 * std::max<int64_t>(host_chunk_cells(), c->ncells);
+  if (pipe) return step_host_pipelined(c, flux, cfl, dx, Qin, Qout, dt_out);
+  if (pipe_ens) return step_host_pipelined_ensemble(c, flux, cfl, dx, Qin, Qout, dt_out);
+  return step_host_plain(c, flux, cfl, dx, Qin, Qout, dt_out);
 }
 
 int hs_host_register(void* ptr, size_t bytes) {

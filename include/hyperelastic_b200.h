@@ -103,6 +103,8 @@ int hs_advance(hs_ctx_t* ctx, int flux, double cfl, double dx, double t_end, int
  * max(lambda) the previous call's fused step produced for the state it returned, the sweep of the uploaded data
  * confirms it bit for bit at the end, and on a mismatch (first call, state edited in between) the step is redone on
  * the device with the right dt -- the result is always bit-identical to hs_upload + hs_step + hs_download.
+ * An ensemble on one device is pipelined the same way by groups of whole problems with per-problem hints (any refuted hint redoes
+ * the step); contexts spanning several devices and odd cell counts take upload + step + download.
  * The copies only overlap from page-locked memory: register the arrays once with hs_host_register (a Julia Array,
  * a numpy array ... are pageable).  HS_HOST_PIPELINE=0 forces upload + step + download; HS_HOST_CHUNK = cells per chunk. */
 int hs_step_host(hs_ctx_t* ctx, int flux, double cfl, double dx, const double* Qin, double* Qout,

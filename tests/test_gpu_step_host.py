@@ -110,3 +110,41 @@ def test_step_host_plain_paths(gpu, oracle):
     with hs.Solver(eos, 1 << 21, model=hm) as ref:
         ref.upload(Q0); ref.advance(1e9, "hll", 0.6, 1.0 / (1 << 21), max_steps=2)
         assert np.array_equal(Q3, ref.download())
+
+
+@pytest.mark.parametrize("model,nx,nprob", [("sp13", 512, 24), ("sp13", 130, 40), ("mph30", 256, 20)])
+def test_pipelined_step_host_ensemble(gpu, small_chunks, model, nx, nprob):
+    """ensembles: groups of whole problems per chunk, per-problem hints; bit-identical to the resident loop, also when one
+    problem of the ensemble is edited between two calls (every hint but one confirmed -> the step is redone)"""
+    hs = gpu
+    from util import random_mph_prims, random_sp_prims
+    rng = np.random.default_rng(nx + nprob)
+    if model == "mph30":
+        eos = (hs.Barton2009(), hs.Barton2009()); hm = hs.MPH30
+        Qlr = hs.prim2cons_mph(eos, random_mph_prims(rng, 2 * nprob, spread=0.03)).reshape(nprob, 2, 30)
+    else:
+        eos = hs.Barton2009(); hm = hs.SP13
+        Qlr = hs.hyperelasticity.prim2cons(eos, random_sp_prims(rng, 2 * nprob, spread=0.03)).reshape(nprob, 2, 13)
+    Q0 = np.where((np.arange(nx) < nx / 2)[None, :, None], Qlr[:, None, 0, :], Qlr[:, None, 1, :]).copy()
+    nsteps = 5
+    with hs.Solver(eos, nx, nprob=nprob, model=hm) as ref:
+        ref.upload(Q0)
+        dts = ref.advance(1e9, "hll", 0.6, 1.0 / nx, max_steps=nsteps, record_dt=True)
+        Qref = ref.download()
+    with hs.Solver(eos, nx, nprob=nprob, model=hm) as sol:
+        Qa = hs.register_host(Q0.copy()); Qb = hs.register_host(np.empty_like(Q0))
+        for k in range(nsteps):
+            _, dt = sol.step_host(Qa, Qb, "hll", 0.6, 1.0 / nx)
+            assert np.array_equal(dt, dts[:, k]), k
+            Qa, Qb = Qb, Qa
+        assert sol.step_host_stats() == (nsteps, nsteps - 1)
+        assert np.array_equal(Qa, Qref)
+        # edit one problem: its hint is refuted, the whole step is redone with the true values
+        Qa[nprob // 2, :, 0 if model == "sp13" else 2] *= 1.5
+        Qe = Qa.copy()
+        sol.step_host(Qa, Qb, "hll", 0.6, 1.0 / nx)
+        assert sol.step_host_stats() == (nsteps + 1, nsteps - 1)
+        hs.unregister_host(Qa); hs.unregister_host(Qb)
+    with hs.Solver(eos, nx, nprob=nprob, model=hm) as ref:
+        ref.upload(Qe); ref.step("hll", 0.6, 1.0 / nx)
+        assert np.array_equal(Qb, ref.download())
