@@ -1204,8 +1204,8 @@ int hs_step_host(hs_ctx_t* c, int flux, double cfl, double dx, const double* Qin
   if (flux != HS_FLUX_HLL && flux != HS_FLUX_LXF) return fail(HS_ERR_ARG, "unknown flux");
   const char* eoff = std::getenv("HS_HOST_PIPELINE");
   const bool off = eoff && eoff[0] == '0';
-  // one grid on one device with at least two chunks: the pipelined form; everything else (ensembles, several devices,
-  // small grids, odd cell counts) takes upload + step + download
+  // one grid on one device (at least half a chunk of cells): the pipelined form; ensembles on one device: the same by groups of whole
+  // problems; everything else (several devices, small grids, odd cell counts) takes upload + step + download
   const bool pipe = !off && c->parts.size() == 1 && c->nprob == 1 && c->ncells % 2 == 0 && c->ncells >= host_chunk_cells() / 2 && c->ncells >= 4096;
   // an ensemble on one device: groups of whole problems, at least two groups (even problem length keeps the groups on the tensor-map copies)
   const bool pipe_ens = !off && c->parts.size() == 1 && c->nprob > 1 && c->ncells % 2 == 0 && c->ncells * c->nprob >= 4096 &&

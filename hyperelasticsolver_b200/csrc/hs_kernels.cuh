@@ -1189,7 +1189,11 @@ __global__ void __launch_bounds__(T, HS_MINB_SP) k_step_sp(const StepArgs g, con
       }
 #pragma unroll
       for (int j = 2; j < 15; ++j) {
-        const double Fa = flux_is_zero(j) ? 0.0 : fa[j], Fb = flux_is_zero(j) ? 0.0 : fb[j];
+        if (flux_is_zero(j)) {   // rho F_1j: the physical flux is identically zero (u1 A_1j - u1 A_1j); only the jump term is left
+          F[j] = (FLUX == FLUX_HLL) ? k_q * (q[j] - ra[j]) : -(0.5 * lambda) * (q[j] - ra[j]);
+          continue;
+        }
+        const double Fa = fa[j], Fb = fb[j];
         if (FLUX == FLUX_HLL) F[j] = fma(s_r, Fa, fma(-s_l, Fb, k_q * (q[j] - ra[j])));      // NumFluxes.jl:78
         else F[j] = 0.5 * (Fa + Fb) - 0.5 * lambda * (q[j] - ra[j]);                          // NumFluxes.jl:30
       }
