@@ -329,6 +329,28 @@ def hll_pathcons(eoss, Ql, Qr, eig_l, eig_r):   # NumFluxes.jl:85-132
     return s_l, s_r, dm, dp
 
 
+def time_step(eoss, cells, cfl, dx):
+    """one pass of the loop body of main.jl:204-227 on a list of 30-vectors: CFL sweep (:204-212), frozen boundary cells (:219-220),
+    update_cell with hll (:43-60, :225).  Returns (new cells, dt)."""
+    eig = []
+    for Q in cells:
+        e = []
+        for p in range(2):
+            e += get_eigvals_phase(eoss[p], Q[15 * p:15 * p + 15])[0]
+        eig.append(e)
+    lam = max(max(abs(x) for x in e) for e in eig)               # main.jl:210-212
+    dt = cfl * dx / lam
+    dtdx = dt / dx
+    faces = [hll_pathcons(eoss, cells[i], cells[i + 1], eig[i], eig[i + 1]) for i in range(len(cells) - 1)]   # (s_l, s_r, D-, D+)
+    new = [list(cells[0])]
+    for i in range(1, len(cells) - 1):
+        NF_l = faces[i - 1][3]      # D+ of the left face   (main.jl:56)
+        NF_r = faces[i][2]          # D- of the right face  (main.jl:57)
+        new.append([cells[i][k] - dtdx * ((0 - 0) + (NF_r[k] + NF_l[k])) for k in range(30)])        # main.jl:59 (hll's conservative part is zero)
+    new.append(list(cells[-1]))
+    return new, dt
+
+
 # ---------------------------------------------------------------------------------------------
 def s30(x):
     return mp.nstr(x, 30, strip_zeros=False, min_fixed=-1000, max_fixed=-999)   # 30 significant digits, exponent form
@@ -366,6 +388,24 @@ def generate(path):
     doc["hll_faces"] = faces
     xs, ws = gauss_legendre6()
     doc["gauss_legendre6"] = {"x": [s30(x) for x in xs], "w": [s30(w) for w in ws]}
+    # two complete time steps (main.jl:204-227) of a 10-cell Riemann grid: test case 6 states with a smooth
+    # transition so that every face has a non-trivial path integral
+    cs = [c for c in src["cases"] if c["eos"] == "default"]
+    eoss = [Barton2009(b) for b in cs[0]["eos_blocks"]]
+    Ql = [mpf(float(x)) for x in cs[0]["Q"]]; Qr = [mpf(float(x)) for x in cs[1]["Q"]]
+    nx = 10
+    cells = []
+    for i in range(nx):
+        w = mpf(i) / (nx - 1)
+        w = float(w * w * (3 - 2 * w))                       # smoothstep, rounded to a double so that the FP64 codes get the same input
+        cells.append([mpf(float((1 - w) * float(a) + w * float(b))) for a, b in zip(Ql, Qr)])
+    start = [[float(x) for x in c] for c in cells]
+    dts = []
+    for _ in range(2):
+        cells, dt = time_step(eoss, cells, mpf(float(0.6)), mpf(float(1.0 / nx)))
+        dts.append(dt)
+    doc["two_steps"] = {"eos_blocks": cs[0]["eos_blocks"], "nx": nx, "cfl": 0.6, "Q0": start, "dt": [s30(x) for x in dts],
+                        "Q": [[s30(x) for x in c] for c in cells]}
     with open(path, "w") as f:
         json.dump(doc, f, indent=0)
     return doc

@@ -336,3 +336,21 @@ def test_mp_restatement_anchors():
     Q = [mp.mpf(float(x)) for x in c["Q"]]
     again = [M.s30(x) for x in M.noncons_cols(eoss, Q)]
     assert again == c["noncons_cols"]
+
+
+def test_oracle_time_step_within_roundoff_of_exact_arithmetic(oracle):
+    """two complete passes of the loop body of main.jl:204-227 (CFL sweep, dt, frozen boundary cells, update_cell with the
+    path-conservative hll on every face) restated independently in 50-digit arithmetic (oracle/mporacle.py::time_step):
+    the C++ oracle's run -- in both of its modes -- reproduces dt and the state to roundoff"""
+    d = json.load(open(os.path.join(G, "mp_vectors.json")))["two_steps"]
+    eos = [np.array(b) for b in d["eos_blocks"]]
+    Q0 = np.array(d["Q0"]); nx = d["nx"]
+    want = np.array([[float(x) for x in c] for c in d["Q"]])
+    dtw = np.array([float(x) for x in d["dt"]])
+    for literal in (False, True):
+        r = oracle.run(eos, oracle.MPH30, oracle.HLL, Q0, d["cfl"], 1.0 / nx, 1e9, 2, literal=literal)
+        assert r["status"] == 0
+        assert np.abs(r["dt"][0] - dtw).max() < 1e-15 * dtw.max()
+        scale = np.maximum(np.abs(want).max(axis=0), 1e-3 * np.abs(want).max())
+        assert (np.abs(r["Q"] - want).max(axis=0) / scale).max() < 5e-14        # measured 1.1e-14
+        assert np.array_equal(r["Q"][0], Q0[0]) and np.array_equal(r["Q"][-1], Q0[-1])      # main.jl:219-220
