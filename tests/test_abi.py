@@ -81,6 +81,15 @@ def test_no_cpu_fallback(hs):
     assert ei.value.code == L.HS_ERR_CUDA
     with pytest.raises(hs.HyperelasticError):
         hs.Solver(eos, 100)
+    with pytest.raises(hs.HyperelasticError) as ei:
+        hs.Solver2D(eos, 16, 16)
+    assert ei.value.code == L.HS_ERR_CUDA
+    with pytest.raises(hs.HyperelasticError) as ei:
+        hs.register_host(np.zeros(64))
+    assert ei.value.code == L.HS_ERR_CUDA
+    # argument errors are reported before any device work
+    assert L.lib().hs_step_host(None, L.HLL, 0.6, 0.1, None, None, None) == L.HS_ERR_ARG
+    assert L.lib().hs2d_step(None, L.HLL, 0.6, 0.1, 0.1, None) == L.HS_ERR_ARG
 
 
 def test_product_does_not_import_oracle():
