@@ -288,7 +288,7 @@ int launch_step_m(int flux, int gen, const StepArgs& a, int64_t nb, cudaStream_t
 
 extern "C" {
 
-const char* hs_version(void) { return "hyperelastic_b200 0.1 (sm_100a)"; }
+const char* hs_version(void) { return "hyperelastic_b200 0.2 (sm_100a)"; }
 const char* hs_last_error(void) { return g_err.c_str(); }
 int64_t hs_kernel_launch_count(void) { return g_launches.load(); }
 
