@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -195,10 +196,15 @@ int sp_tiles_per_block(int64_t ntiles) {
   int64_t k;
   if (const char* e = std::getenv("HS_SP_TILES")) {
     k = std::atoi(e);
-    if (k > 64) k = 64;
+    if (k > 4096) k = 4096;
   } else {
+    // at least two blocks per resident slot, at most ~sqrt(ntiles)/30 tiles per block (12 at 2^24 cells, 24 from 2^26 on): longer
+    // blocks amortise the unprefetched first tile, shorter ones keep the tail of the launch short (measured: profiles/r02_experiments.md)
     k = ntiles / (2 * 4 * 148);
-    if (k > 8) k = 8;
+    int64_t cap = (int64_t)(std::sqrt((double)ntiles) / 30.0);
+    if (cap < 8) cap = 8;
+    if (cap > 24) cap = 24;
+    if (k > cap) k = cap;
   }
   if (k > ntiles) k = ntiles;
   if (k < 1) k = 1;
