@@ -276,7 +276,7 @@ int64_t qp_max_cells() {
 
 template <int MODEL, int T>
 int launch_step_m(int flux, int gen, const StepArgs& a, int64_t nb, cudaStream_t st) {
-  if (MODEL == MODEL_SP13) {
+  if constexpr (MODEL == MODEL_SP13) {
     // the pipeline needs 16-byte aligned array bases (any cudaMalloc / torch allocation); HS_SP_TMA=0 forces the plain kernel
     const char* e = std::getenv("HS_SP_TMA");
     const bool aligned = ((reinterpret_cast<uintptr_t>(a.Qin) | reinterpret_cast<uintptr_t>(a.aux_in)) & 15u) == 0;
